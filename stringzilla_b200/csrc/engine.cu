@@ -1,0 +1,1081 @@
+/**
+ *  @file engine.cu
+ *  @brief Host side of `libstringzillas_b200.so`: engines, device scopes, input staging, the slot/job scheduler and
+ *         the `szs_*` C ABI declared in include/stringzillas_b200.h.
+ *
+ *  Mirrors the roles (not the code) of the reference's C shims and CUDA engine drivers:
+ *    c/stringzillas/{runtime,levenshtein,needleman_wunsch,smith_waterman}.cuh and
+ *    include/stringzillas/similarities/cuda.cuh:4247-4417 (`cross_`), 5913-6032 (`cuda_weighted_cross_`).
+ *  Where the reference materialises one 112-byte task per matrix cell, sorts tasks through six tiers with host
+ *  round-trips and scatters results (cuda.cuh:1653-1711, 1916-1955, 4394-4401), this driver keeps the work list at
+ *  O(candidates): candidates are sorted by length and paired into slots, each slot is crossed with blocks of queries,
+ *  and persistent CTAs drain that job list through one atomic counter. Results are written in place by the kernel.
+ *
+ *  There is NO CPU fallback in this file: without a usable sm_100-class device every scoring call fails loudly.
+ */
+#include "../../include/stringzillas_b200.h"
+#include "launch.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace szb {
+
+#pragma region Helper kernels
+
+/** Maps raw bytes through a 256-entry class table (NW/SW: the engine's `byte_to_class`; Levenshtein: the alphabet). */
+__global__ void map_classes_kernel(uint8_t const *in, uint8_t *out, uint64_t n, uint8_t const *lut) {
+    __shared__ uint8_t table[256];
+    if (threadIdx.x < 256) table[threadIdx.x] = lut[threadIdx.x];
+    __syncthreads();
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x * 16;
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16; base < n; base += stride) {
+        if (base + 16 <= n) {
+            uint4 v = *(uint4 const *)(in + base); // staging buffers are 256-byte aligned
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                w[i] = (uint32_t)table[w[i] & 0xFF] | ((uint32_t)table[(w[i] >> 8) & 0xFF] << 8) |
+                       ((uint32_t)table[(w[i] >> 16) & 0xFF] << 16) | ((uint32_t)table[w[i] >> 24] << 24);
+            *(uint4 *)(out + base) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        else {
+            for (uint64_t i = base; i < n; ++i) out[i] = table[in[i]];
+        }
+    }
+}
+
+/** Marks which byte values occur in a blob: flags[b] != 0. Drives the Levenshtein alphabet compaction. */
+__global__ void byte_presence_kernel(uint8_t const *in, uint64_t n, uint32_t *flags) {
+    __shared__ uint32_t seen[256];
+    if (threadIdx.x < 256) seen[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) seen[in[i]] = 1;
+    __syncthreads();
+    if (threadIdx.x < 256 && seen[threadIdx.x]) flags[threadIdx.x] = 1;
+}
+
+/** Symmetric mode: mirror the lower triangle (query i, candidate j < i) into the upper one (serial.hpp:3183-3184). */
+__global__ void mirror_lower_kernel(int64_t *results, uint64_t n, uint64_t stride) {
+    uint64_t const total = n * n;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t const i = idx / n, j = idx % n;
+        if (j > i) results[i * stride + j] = results[j * stride + i];
+    }
+}
+
+#pragma endregion
+
+#pragma region Errors
+
+struct Failure {
+    sz_status_t status = sz_success_k;
+    char const *message = nullptr;
+    explicit operator bool() const { return status != sz_success_k; }
+};
+
+static Failure ok() { return {}; }
+static Failure fail(sz_status_t status, char const *message) { return {status, message}; }
+static Failure fail_cuda(cudaError_t error) {
+    // cudaGetErrorName returns a static string, like the reference's `cuGetErrorName` path (stringzillas.cuh:236-257).
+    if (error == cudaErrorMemoryAllocation) return {sz_bad_alloc_k, cudaGetErrorName(error)};
+    if (error == cudaErrorNoDevice || error == cudaErrorInsufficientDriver || error == cudaErrorInvalidDevice)
+        return {sz_missing_gpu_k, cudaGetErrorName(error)};
+    return {sz_status_unknown_k, cudaGetErrorName(error)};
+}
+#define SZB_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t error_ = (call);                     \
+        if (error_ != cudaSuccess) {                     \
+            cudaGetLastError();                          \
+            return fail_cuda(error_);                    \
+        }                                                \
+    } while (0)
+
+static sz_status_t report(Failure failure, char const **error_message) {
+    if (error_message) *error_message = failure.status == sz_success_k ? nullptr : failure.message;
+    return failure.status;
+}
+
+#pragma endregion
+
+#pragma region Device memory
+
+/** Grow-only device allocation, like the reference's engine-owned `cuda_cross_buffers` (cuda.cuh:1724-1775). */
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t capacity = 0;
+    DeviceBuffer() = default;
+    DeviceBuffer(DeviceBuffer const &) = delete;
+    DeviceBuffer &operator=(DeviceBuffer const &) = delete;
+    ~DeviceBuffer() {
+        if (ptr) cudaFree(ptr);
+    }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= capacity) return cudaSuccess;
+        if (ptr) cudaFree(ptr), ptr = nullptr, capacity = 0;
+        size_t const rounded = ((bytes + bytes / 4 + 4095) / 4096) * 4096;
+        cudaError_t error = cudaMalloc(&ptr, rounded);
+        if (error == cudaSuccess) capacity = rounded;
+        return error;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+/** Grow-only pinned host arena for the small per-call uploads (offsets, slots, jobs, query order). */
+struct PinnedBuffer {
+    void *ptr = nullptr;
+    size_t capacity = 0;
+    ~PinnedBuffer() {
+        if (ptr) cudaFreeHost(ptr);
+    }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= capacity) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr), ptr = nullptr, capacity = 0;
+        size_t const rounded = ((bytes + bytes / 4 + 4095) / 4096) * 4096;
+        cudaError_t error = cudaMallocHost(&ptr, rounded);
+        if (error == cudaSuccess) capacity = rounded;
+        return error;
+    }
+};
+
+#pragma endregion
+
+#pragma region Device scopes
+
+/** Reference: `device_scope_t` = variant<default, cpu, gpu> (c/stringzillas/stringzillas.cuh:275-332). */
+struct Scope {
+    enum Kind { kDefault, kCpu, kGpu } kind = kDefault;
+    size_t cpu_cores = 1;
+    int gpu_device = 0;
+    cudaStream_t stream = nullptr; // created lazily on first use, one stream per scope (types.cuh:403-473)
+    std::mutex mutex;
+
+    ~Scope() {
+        if (stream) {
+            cudaSetDevice(gpu_device);
+            cudaStreamDestroy(stream);
+        }
+    }
+    Failure ensure_stream() {
+        std::lock_guard<std::mutex> lock(mutex);
+        SZB_CUDA(cudaSetDevice(gpu_device));
+        if (!stream) SZB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        return ok();
+    }
+};
+
+static int visible_device_count() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
+
+/** Compute capability major*10+minor of a device, or 0. */
+static int device_sm_code(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return prop.major * 10 + prop.minor;
+}
+
+#pragma endregion
+
+#pragma region Inputs
+
+/** A string collection as the three ABI layouts present it, normalised to: bytes + 32-bit offsets. */
+struct InputView {
+    enum Layout { kSequence, kTape32, kTape64 } layout = kTape64;
+    void const *object = nullptr;
+    size_t count() const {
+        switch (layout) {
+        case kSequence: return (size_t) static_cast<sz_sequence_t const *>(object)->count;
+        case kTape32: return (size_t) static_cast<sz_sequence_u32tape_t const *>(object)->count;
+        default: return (size_t) static_cast<sz_sequence_u64tape_t const *>(object)->count;
+        }
+    }
+};
+
+static bool pointer_is_host_readable(void const *pointer) {
+    if (!pointer) return true;
+    cudaPointerAttributes attributes;
+    if (cudaPointerGetAttributes(&attributes, pointer) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attributes.type != cudaMemoryTypeDevice;
+}
+
+/** One side of the cross product, staged on the device. */
+struct StagedSet {
+    size_t count = 0;
+    uint64_t total_bytes = 0;
+    std::vector<uint32_t> offsets; // count + 1, relative to the staged blob
+    uint32_t longest = 0;
+    DeviceBuffer raw, classes, device_offsets;
+    PinnedBuffer gather; // only for callback sequences
+    std::vector<uint8_t> offsets_bounce;
+};
+
+#pragma endregion
+
+#pragma region Engines
+
+enum class Algorithm { kLevenshtein = 0, kNeedlemanWunsch = 1, kSmithWaterman = 2 };
+
+struct Engine {
+    Algorithm algorithm = Algorithm::kLevenshtein;
+    // Costs exactly as the caller passed them (reference conventions).
+    int match = 0, mismatch = 1, open = 1, extend = 1;
+    uint8_t byte_to_class[256] = {0};
+    int8_t costs[32 * 32] = {0};
+
+    // Grow-only device state, one set per engine: engines are not re-entrant.
+    StagedSet queries, candidates;
+    DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch;
+    PinnedBuffer upload, upload_model;
+    cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
+    int events_device = -1;
+    szs_b200_call_stats_t stats = {};
+    std::mutex mutex;
+
+    ~Engine() {
+        for (cudaEvent_t event : events)
+            if (event) cudaEventDestroy(event);
+    }
+};
+
+#pragma endregion
+
+#pragma region Staging
+
+/** Copies one collection to the device: raw bytes + offsets. Accepts host, pinned, managed or device memory. */
+static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, szs_b200_call_stats_t &stats) {
+    size_t const count = view.count();
+    set.count = count;
+    set.offsets.resize(count + 1);
+    set.longest = 0;
+    uint8_t const *blob = nullptr;
+    bool contiguous = true;
+
+    if (view.layout == InputView::kTape32 || view.layout == InputView::kTape64) {
+        void const *offsets_pointer;
+        size_t offset_width;
+        if (view.layout == InputView::kTape32) {
+            auto const *tape = static_cast<sz_sequence_u32tape_t const *>(view.object);
+            blob = (uint8_t const *)tape->data, offsets_pointer = tape->offsets, offset_width = 4;
+        }
+        else {
+            auto const *tape = static_cast<sz_sequence_u64tape_t const *>(view.object);
+            blob = (uint8_t const *)tape->data, offsets_pointer = tape->offsets, offset_width = 8;
+        }
+        if (count == 0) {
+            set.offsets[0] = 0, set.total_bytes = 0;
+        }
+        else {
+            if (!offsets_pointer) return fail(sz_unexpected_dimensions_k, "Tape offsets are null");
+            // Offsets are read on the host (as the reference does, cuda.cuh:4285-4295); bounce device-only ones.
+            void const *host_offsets = offsets_pointer;
+            if (!pointer_is_host_readable(offsets_pointer)) {
+                set.offsets_bounce.resize((count + 1) * offset_width);
+                SZB_CUDA(cudaMemcpyAsync(set.offsets_bounce.data(), offsets_pointer, (count + 1) * offset_width,
+                                         cudaMemcpyDeviceToHost, stream));
+                SZB_CUDA(cudaStreamSynchronize(stream));
+                host_offsets = set.offsets_bounce.data();
+            }
+            uint64_t first, last;
+            if (offset_width == 4) {
+                auto const *o = static_cast<uint32_t const *>(host_offsets);
+                first = o[0], last = o[count];
+                if (last < first || last - first > 0xFFFFFFF0ull)
+                    return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
+                for (size_t i = 0; i <= count; ++i) set.offsets[i] = o[i] - (uint32_t)first;
+            }
+            else {
+                auto const *o = static_cast<uint64_t const *>(host_offsets);
+                first = o[0], last = o[count];
+                if (last < first || last - first > 0xFFFFFFF0ull)
+                    return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
+                for (size_t i = 0; i <= count; ++i) set.offsets[i] = (uint32_t)(o[i] - first);
+            }
+            set.total_bytes = last - first;
+            blob += first;
+        }
+    }
+    else {
+        auto const *sequence = static_cast<sz_sequence_t const *>(view.object);
+        contiguous = false;
+        uint64_t running = 0;
+        for (size_t i = 0; i < count; ++i) {
+            set.offsets[i] = (uint32_t)running;
+            running += sequence->get_length(sequence->handle, i);
+            if (running > 0xFFFFFFF0ull) return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
+        }
+        set.offsets[count] = (uint32_t)running;
+        set.total_bytes = running;
+    }
+    for (size_t i = 0; i < count; ++i) {
+        if (set.offsets[i + 1] < set.offsets[i]) return fail(sz_unexpected_dimensions_k, "Tape offsets decrease");
+        set.longest = std::max(set.longest, set.offsets[i + 1] - set.offsets[i]);
+    }
+
+    // Padding keeps the 16-byte vector loads of the class-mapping kernel in bounds.
+    SZB_CUDA(set.raw.reserve(set.total_bytes + 256));
+    SZB_CUDA(set.classes.reserve(set.total_bytes + 256));
+    SZB_CUDA(set.device_offsets.reserve((count + 1) * sizeof(uint32_t)));
+    if (set.total_bytes) {
+        if (contiguous) {
+            SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, blob, set.total_bytes, cudaMemcpyDefault, stream));
+            if (pointer_is_host_readable(blob)) stats.h2d_bytes += set.total_bytes;
+        }
+        else {
+            auto const *sequence = static_cast<sz_sequence_t const *>(view.object);
+            sz_cptr_t const first = sequence->get_start(sequence->handle, 0);
+            if (pointer_is_host_readable(first)) {
+                SZB_CUDA(set.gather.reserve(set.total_bytes));
+                for (size_t i = 0; i < count; ++i) {
+                    size_t const length = set.offsets[i + 1] - set.offsets[i];
+                    if (length)
+                        std::memcpy((char *)set.gather.ptr + set.offsets[i], sequence->get_start(sequence->handle, i),
+                                    length);
+                }
+                SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, set.gather.ptr, set.total_bytes, cudaMemcpyHostToDevice,
+                                         stream));
+                stats.h2d_bytes += set.total_bytes;
+            }
+            else {
+                for (size_t i = 0; i < count; ++i) {
+                    size_t const length = set.offsets[i + 1] - set.offsets[i];
+                    if (length)
+                        SZB_CUDA(cudaMemcpyAsync((char *)set.raw.ptr + set.offsets[i],
+                                                 sequence->get_start(sequence->handle, i), length, cudaMemcpyDefault,
+                                                 stream));
+                }
+            }
+        }
+    }
+    SZB_CUDA(cudaMemcpyAsync(set.device_offsets.ptr, set.offsets.data(), (count + 1) * sizeof(uint32_t),
+                             cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += (count + 1) * sizeof(uint32_t);
+    return ok();
+}
+
+#pragma endregion
+
+#pragma region Scheduling
+
+/** Everything the host decides about one call's scoring model. */
+struct Model {
+    Scoring scoring;        // uploaded verbatim
+    uint8_t lut[256];       // byte -> class (identity in compare mode)
+    int family16 = -1;      // packed family, or -1 when the cost signs rule the packed recurrences out
+    int family32 = 0;       // 32-bit family, always available
+    int64_t range_offset = 0;   // 16-bit tier: constant part of the largest cell value
+    int64_t range_per_step = 0; // 16-bit tier: growth per min(query, candidate) character
+    bool symmetric_costs = true;
+};
+
+/**
+ *  Translates the engine's costs into the kernels' maximising convention and decides which recurrence families
+ *  are exact for them. `present` flags the byte values occurring among the candidates (Levenshtein only).
+ */
+static void build_model(Engine const &engine, uint32_t const *present, Model &model) {
+    Scoring &sc = model.scoring;
+    std::memset(&sc, 0, sizeof(sc));
+    bool const local = engine.algorithm == Algorithm::kSmithWaterman;
+    bool linear = engine.open == engine.extend;
+    int smin = 127, smax = -128;
+
+    if (engine.algorithm == Algorithm::kLevenshtein) {
+        // Distances are minimised: negate every cost, maximise, negate the result.
+        sc.negate = 1;
+        sc.open = -engine.open, sc.extend = -engine.extend;
+        sc.match = -engine.match, sc.mismatch = -engine.mismatch;
+        int distinct = 0;
+        for (int b = 0; b < 256; ++b) distinct += present[b] != 0;
+        if (distinct <= 31) {
+            int next = 0;
+            for (int b = 0; b < 256; ++b) model.lut[b] = present[b] ? (uint8_t)next++ : (uint8_t)distinct;
+            sc.n_classes = distinct + 1; // the last class collects query bytes no candidate contains
+            for (int a = 0; a < 32; ++a)
+                for (int b = 0; b < 32; ++b)
+                    sc.sub[a * 32 + b] = (int8_t)((a == b && a < distinct) ? sc.match : sc.mismatch);
+            smin = std::min(sc.match, sc.mismatch), smax = std::max(sc.match, sc.mismatch);
+        }
+        else {
+            for (int b = 0; b < 256; ++b) model.lut[b] = (uint8_t)b;
+            sc.compare = 1, sc.n_classes = 0;
+            smin = std::min(sc.match, sc.mismatch), smax = std::max(sc.match, sc.mismatch);
+        }
+    }
+    else {
+        sc.open = engine.open, sc.extend = engine.extend;
+        int top = 0;
+        for (int b = 0; b < 256; ++b) model.lut[b] = engine.byte_to_class[b] & 31, top = std::max<int>(top, model.lut[b]);
+        sc.n_classes = top + 1;
+        std::memcpy(sc.sub, engine.costs, sizeof(sc.sub));
+        for (int a = 0; a <= top; ++a)
+            for (int b = 0; b <= top; ++b) {
+                smin = std::min<int>(smin, sc.sub[a * 32 + b]), smax = std::max<int>(smax, sc.sub[a * 32 + b]);
+                if (sc.sub[a * 32 + b] != sc.sub[b * 32 + a]) model.symmetric_costs = false;
+            }
+    }
+
+    model.family32 = local ? (linear ? FAM_S32_LOCAL_LIN : FAM_S32_LOCAL_AFF)
+                           : (linear ? FAM_S32_GLOBAL_LIN : FAM_S32_GLOBAL_AFF);
+    model.family16 = -1;
+    if (sc.compare) return; // large alphabets: byte-compare recurrences exist only in the 32-bit tier for now
+
+    int const open = sc.open, extend = sc.extend;
+    if (!local && linear) {
+        // u = H - (i + j) * g, e = max(S - 2g, 0): exact for every sign of g. Cells stay below min(m, n) * e_max.
+        model.family16 = FAM_LIN_SHIFT;
+        sc.bias = 0;
+        model.range_offset = 0, model.range_per_step = std::max(smax - 2 * open, 0);
+    }
+    else if (!local && extend <= 0 && extend - open >= 0) {
+        // The finite "discard" seeds of the reference's Gotoh baselines equal -inf seeds iff extend <= 0.
+        int const go = extend - open;
+        model.family16 = FAM_AFF_SHIFT;
+        sc.bias = 4 * go;
+        model.range_offset = 4 * go, model.range_per_step = std::max(std::max(smax, 2 * open) - 2 * extend, 0);
+    }
+    else if (local && linear && open <= 0) {
+        model.family16 = FAM_SW_LIN;
+        sc.bias = std::max(std::max(-smin, -open), 0);
+        model.range_offset = sc.bias, model.range_per_step = std::max(smax, 0);
+    }
+    else if (local && !linear && open <= 0 && extend <= 0) {
+        model.family16 = FAM_SW_AFF;
+        sc.bias = std::max(std::max(-smin, -(open + 2 * extend)), std::max(-open, 0));
+        model.range_offset = sc.bias, model.range_per_step = std::max(smax, 0);
+    }
+}
+
+/** Whether every cell (and the retired intermediate of one more step) of a pair fits an unsigned 16-bit half. */
+static bool fits_u16(Model const &model, uint64_t shorter) {
+    if (model.family16 < 0) return false;
+    return (uint64_t)model.range_offset + (shorter + 2) * (uint64_t)model.range_per_step <= 65000ull;
+}
+
+/** Whether the 32-bit tier is exact: |score| <= (m + n + 4) * magnitude must stay far from 2^31 (and the 2^28 pad). */
+static bool fits_s32(Engine const &engine, uint64_t total_length) {
+    int magnitude = 1;
+    if (engine.algorithm == Algorithm::kLevenshtein)
+        magnitude = std::max(std::max(std::abs(engine.match), std::abs(engine.mismatch)),
+                             std::max(std::abs(engine.open), std::abs(engine.extend)));
+    else {
+        magnitude = std::max(std::abs(engine.open), std::abs(engine.extend));
+        for (int i = 0; i < 32 * 32; ++i) magnitude = std::max<int>(magnitude, std::abs(engine.costs[i]));
+    }
+    magnitude = std::max(magnitude, 1);
+    return (total_length + 4) * (uint64_t)magnitude < (1ull << 27);
+}
+
+struct LaunchPlan {
+    int family, shape;
+    uint32_t first_job, n_jobs;
+};
+
+#pragma endregion
+
+#pragma region The cross product
+
+static Failure ensure_events(Engine &engine, int device) {
+    if (engine.events_device == device && engine.events[0]) return ok();
+    for (cudaEvent_t &event : engine.events) {
+        if (event) cudaEventDestroy(event), event = nullptr;
+        SZB_CUDA(cudaEventCreate(&event));
+    }
+    engine.events_device = device;
+    return ok();
+}
+
+/**
+ *  @brief Scores query rows [row_begin, row_end) against every candidate and writes `results[q * stride + c]`.
+ *         `candidates.object == nullptr` requests the symmetric self-similarity of the queries.
+ */
+static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
+                     size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
+    if (scope.kind == Scope::kCpu)
+        return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
+    if (visible_device_count() <= scope.gpu_device) return fail(sz_missing_gpu_k, "No CUDA device is visible");
+    if (device_sm_code(scope.gpu_device) < 100)
+        return fail(sz_missing_gpu_k, "stringzillas_b200 kernels require an sm_100-class (Blackwell) device");
+    if (Failure failure = scope.ensure_stream()) return failure;
+    cudaStream_t const stream = scope.stream;
+    std::lock_guard<std::mutex> engine_lock(engine.mutex);
+    if (Failure failure = ensure_events(engine, scope.gpu_device)) return failure;
+
+    bool const symmetric = candidates_view.object == nullptr;
+    szs_b200_call_stats_t stats = {};
+    SZB_CUDA(cudaEventRecord(engine.events[0], stream));
+
+    // 1. Stage both sides.
+    if (Failure failure = stage_set(queries_view, engine.queries, stream, stats)) return failure;
+    StagedSet &qs = engine.queries;
+    if (!symmetric)
+        if (Failure failure = stage_set(candidates_view, engine.candidates, stream, stats)) return failure;
+    StagedSet &cs = symmetric ? engine.queries : engine.candidates;
+
+    size_t const n_queries = qs.count, n_candidates = cs.count;
+    if (whole_matrix) row_begin = 0, row_end = n_queries;
+    if (row_end > n_queries || row_begin > row_end) return fail(sz_unexpected_dimensions_k, "Row range out of bounds");
+    if (n_candidates && stride < n_candidates)
+        return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
+    size_t const n_rows = row_end - row_begin;
+    if (n_rows == 0 || n_candidates == 0) {
+        SZB_CUDA(cudaStreamSynchronize(stream));
+        engine.stats = stats;
+        return ok();
+    }
+    if (!results) return fail(sz_unexpected_dimensions_k, "Results pointer is null");
+    if (n_queries >= 0xFFFFFFF0ull || n_candidates >= 0xFFFFFFF0ull)
+        return fail(sz_overflow_risk_k, "Too many strings for one call");
+
+    // 2. The scoring model; Levenshtein compacts the alphabet of the candidates into <= 31 classes.
+    uint32_t present[256] = {0};
+    if (engine.algorithm == Algorithm::kLevenshtein) {
+        SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
+        SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
+        if (cs.total_bytes) {
+            byte_presence_kernel<<<296, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
+                                                          engine.flags.as<uint32_t>());
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
+        }
+        SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += sizeof(present);
+    }
+    Model model;
+    build_model(engine, present, model);
+    if (!fits_s32(engine, (uint64_t)qs.longest + cs.longest))
+        return fail(sz_overflow_risk_k, "Pair too long for 32-bit DP cells");
+
+    SZB_CUDA(engine.scoring.reserve(sizeof(Scoring)));
+    SZB_CUDA(engine.lut.reserve(256));
+    SZB_CUDA(engine.upload_model.reserve(sizeof(Scoring) + 256));
+    std::memcpy(engine.upload_model.ptr, &model.scoring, sizeof(Scoring));
+    std::memcpy((char *)engine.upload_model.ptr + sizeof(Scoring), model.lut, 256);
+    SZB_CUDA(cudaMemcpyAsync(engine.scoring.ptr, engine.upload_model.ptr, sizeof(Scoring), cudaMemcpyHostToDevice,
+                             stream));
+    SZB_CUDA(cudaMemcpyAsync(engine.lut.ptr, (char *)engine.upload_model.ptr + sizeof(Scoring), 256,
+                             cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += sizeof(Scoring) + 256;
+
+    // 3. Bytes -> classes (skipped in compare mode, where the kernels read raw bytes).
+    uint8_t const *q_classes = qs.raw.as<uint8_t>(), *c_classes = cs.raw.as<uint8_t>();
+    if (!model.scoring.compare) {
+        auto map_set = [&](StagedSet &set) -> Failure {
+            if (!set.total_bytes) return ok();
+            uint64_t const vectors = (set.total_bytes + 15) / 16;
+            int const blocks = (int)std::min<uint64_t>((vectors + 255) / 256, 148 * 8);
+            map_classes_kernel<<<blocks, 256, 0, stream>>>(set.raw.as<uint8_t>(), set.classes.as<uint8_t>(),
+                                                           set.total_bytes, engine.lut.as<uint8_t>());
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
+            return ok();
+        };
+        if (Failure failure = map_set(qs)) return failure;
+        if (!symmetric)
+            if (Failure failure = map_set(cs)) return failure;
+        q_classes = qs.classes.as<uint8_t>(), c_classes = cs.classes.as<uint8_t>();
+    }
+
+    // 4. Query order: longest first, so that the batches a warp sweeps together have similar lengths and the heavy
+    //    jobs start early.
+    std::vector<uint32_t> order(n_rows);
+    std::iota(order.begin(), order.end(), (uint32_t)row_begin);
+    auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return query_length(a) > query_length(b); });
+    uint32_t const longest_query = query_length(order[0]);
+
+    // 5. Slots: candidates sorted by length; neighbours share a register in the packed tier.
+    std::vector<uint32_t> by_length(n_candidates);
+    std::iota(by_length.begin(), by_length.end(), 0u);
+    auto candidate_length = [&](uint32_t c) { return cs.offsets[c + 1] - cs.offsets[c]; };
+    std::stable_sort(by_length.begin(), by_length.end(),
+                     [&](uint32_t a, uint32_t b) { return candidate_length(a) < candidate_length(b); });
+
+    struct HostSlot {
+        CandSlot slot;
+        int family, shape;
+    };
+    std::vector<HostSlot> host_slots;
+    host_slots.reserve(n_candidates);
+    uint64_t cells_total = 0, cells_u16 = 0;
+    uint64_t query_bytes_in_rows = 0;
+    for (uint32_t q : order) query_bytes_in_rows += query_length(q);
+    for (size_t i = 0; i < n_candidates;) {
+        uint32_t const c0 = by_length[i], len0 = candidate_length(c0);
+        bool const narrow0 = fits_u16(model, std::min<uint64_t>(len0, longest_query));
+        if (narrow0 && i + 1 < n_candidates) {
+            uint32_t const c1 = by_length[i + 1], len1 = candidate_length(c1);
+            if (fits_u16(model, std::min<uint64_t>(len1, longest_query))) {
+                host_slots.push_back({{c0, c1, len0, len1}, model.family16, shape_for_length(len1)});
+                cells_u16 += ((uint64_t)len0 + len1) * query_bytes_in_rows;
+                i += 2;
+                continue;
+            }
+        }
+        host_slots.push_back(
+            {{c0, kNoCandidate, len0, 0}, narrow0 ? model.family16 : model.family32, shape_for_length(len0)});
+        if (narrow0) cells_u16 += (uint64_t)len0 * query_bytes_in_rows;
+        i += 1;
+    }
+    for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
+
+    // 6. Jobs: every slot crossed with blocks of the query order; grouped into one launch per (family, shape).
+    int device_sms = 148;
+    cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, scope.gpu_device);
+    std::vector<Job> host_jobs;
+    std::vector<LaunchPlan> plans;
+    uint64_t scratch_words_per_cta = 0;
+    // Longest slots first: their jobs are the heaviest.
+    std::vector<uint32_t> slot_order(host_slots.size());
+    std::iota(slot_order.begin(), slot_order.end(), 0u);
+    for (int family = 0; family < 8; ++family) {
+        for (int shape = kShapeCount - 1; shape >= 0; --shape) {
+            std::vector<uint32_t> members;
+            for (uint32_t s = (uint32_t)host_slots.size(); s-- > 0;)
+                if (host_slots[s].family == family && host_slots[s].shape == shape) members.push_back(s);
+            if (members.empty()) continue;
+            int const groups = 32 / kShapes[shape].g;
+            uint32_t const min_block = (uint32_t)(kThreads / 32) * groups; // one batch for every warp
+            uint64_t const target_jobs = (uint64_t)device_sms * 8;
+            uint64_t blocks = (target_jobs + members.size() - 1) / members.size();
+            blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (n_rows + min_block - 1) / min_block));
+            uint32_t const block_rows = (uint32_t)((n_rows + blocks - 1) / blocks);
+            LaunchPlan plan = {family, shape, (uint32_t)host_jobs.size(), 0};
+            bool const affine = family_is_affine(family);
+            for (uint32_t begin = 0; begin < n_rows; begin += block_rows) {
+                uint32_t const end = (uint32_t)std::min<uint64_t>(n_rows, (uint64_t)begin + block_rows);
+                for (uint32_t s : members) {
+                    CandSlot const &slot = host_slots[s].slot;
+                    uint32_t const longest = std::max(slot.len0, slot.len1);
+                    uint32_t scratch_words = 0;
+                    if (longest > (uint32_t)kShapes[shape].cols()) {
+                        uint64_t const rows = (uint64_t)query_length(order[begin]) + 1;
+                        uint64_t const words = (uint64_t)(end - begin) * rows * (affine ? 2 : 1);
+                        if (words > 0xFFFFFFFFull) return fail(sz_overflow_risk_k, "Boundary scratch too large");
+                        scratch_words = (uint32_t)words;
+                        scratch_words_per_cta = std::max<uint64_t>(scratch_words_per_cta, words);
+                    }
+                    host_jobs.push_back({s, begin, end, scratch_words});
+                }
+            }
+            plan.n_jobs = (uint32_t)host_jobs.size() - plan.first_job;
+            plans.push_back(plan);
+        }
+    }
+
+    // 7. Upload the work list.
+    std::vector<CandSlot> device_slots(host_slots.size());
+    for (size_t s = 0; s < host_slots.size(); ++s) device_slots[s] = host_slots[s].slot;
+    size_t const order_bytes = order.size() * sizeof(uint32_t), slots_bytes = device_slots.size() * sizeof(CandSlot),
+                 jobs_bytes = host_jobs.size() * sizeof(Job);
+    SZB_CUDA(engine.order.reserve(order_bytes));
+    SZB_CUDA(engine.slots.reserve(slots_bytes));
+    SZB_CUDA(engine.jobs.reserve(jobs_bytes));
+    SZB_CUDA(engine.counters.reserve(plans.size() * sizeof(uint32_t) + 64));
+    SZB_CUDA(engine.upload.reserve(order_bytes + slots_bytes + jobs_bytes));
+    {
+        char *arena = (char *)engine.upload.ptr;
+        size_t cursor = 0;
+        std::memcpy(arena + cursor, order.data(), order_bytes);
+        SZB_CUDA(cudaMemcpyAsync(engine.order.ptr, arena + cursor, order_bytes, cudaMemcpyHostToDevice, stream));
+        cursor += order_bytes;
+        std::memcpy(arena + cursor, device_slots.data(), slots_bytes);
+        SZB_CUDA(cudaMemcpyAsync(engine.slots.ptr, arena + cursor, slots_bytes, cudaMemcpyHostToDevice, stream));
+        cursor += slots_bytes;
+        std::memcpy(arena + cursor, host_jobs.data(), jobs_bytes);
+        SZB_CUDA(cudaMemcpyAsync(engine.jobs.ptr, arena + cursor, jobs_bytes, cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += order_bytes + slots_bytes + jobs_bytes;
+    }
+    SZB_CUDA(cudaMemsetAsync(engine.counters.ptr, 0, plans.size() * sizeof(uint32_t) + 64, stream));
+    SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
+    if (scratch_words_per_cta) SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms));
+
+    // 8. Launch: one persistent grid per (family, shape), all on the scope's stream.
+    SZB_CUDA(cudaEventRecord(engine.events[1], stream));
+    for (size_t p = 0; p < plans.size(); ++p) {
+        LaunchPlan const &plan = plans[p];
+        KernelArgs args;
+        args.q_cls = q_classes, args.q_off = qs.device_offsets.as<uint32_t>();
+        args.c_cls = c_classes, args.c_off = cs.device_offsets.as<uint32_t>();
+        args.q_order = engine.order.as<uint32_t>();
+        args.slots = engine.slots.as<CandSlot>();
+        args.jobs = engine.jobs.as<Job>() + plan.first_job;
+        args.n_jobs = plan.n_jobs;
+        args.job_counter = engine.counters.as<uint32_t>() + p;
+        args.scoring = engine.scoring.as<Scoring>();
+        args.results = engine.results.as<int64_t>();
+        args.stride = n_candidates;
+        args.row_base = (uint32_t)row_begin;
+        args.scratch = engine.scratch.as<uint32_t>();
+        args.scratch_words_per_cta = scratch_words_per_cta;
+        int const grid = (int)std::min<uint32_t>(plan.n_jobs, (uint32_t)device_sms);
+        size_t const smem = shared_bytes(plan.shape, model.scoring.n_classes, model.scoring.compare != 0);
+        SZB_CUDA(launch_wavefront(plan.family, plan.shape, grid, smem, stream, args));
+        stats.kernel_launches++;
+    }
+    if (symmetric && whole_matrix && n_queries > 1) {
+        uint64_t const total = (uint64_t)n_queries * n_queries;
+        int const blocks = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);
+        mirror_lower_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates);
+        SZB_CUDA(cudaGetLastError());
+        stats.kernel_launches++;
+    }
+    SZB_CUDA(cudaEventRecord(engine.events[2], stream));
+
+    // 9. Results home: a strided 2-D copy into the caller's matrix (host, pinned, managed or device memory).
+    SZB_CUDA(cudaMemcpy2DAsync((int64_t *)results + row_begin * stride, stride * sizeof(int64_t), engine.results.ptr,
+                               n_candidates * sizeof(int64_t), n_candidates * sizeof(int64_t), n_rows,
+                               cudaMemcpyDefault, stream));
+    if (pointer_is_host_readable(results)) stats.d2h_bytes += n_rows * n_candidates * sizeof(int64_t);
+    SZB_CUDA(cudaEventRecord(engine.events[3], stream));
+    SZB_CUDA(cudaStreamSynchronize(stream));
+
+    float kernel_ms = 0, total_ms = 0;
+    cudaEventElapsedTime(&kernel_ms, engine.events[1], engine.events[2]);
+    cudaEventElapsedTime(&total_ms, engine.events[0], engine.events[3]);
+    stats.kernel_milliseconds = kernel_ms, stats.total_milliseconds = total_ms;
+    stats.cells = cells_total;
+    if (symmetric && whole_matrix) {
+        // Only the lower triangle (with the diagonal) counts as scored work, as in bench/similarities.cuh:344-363.
+        uint64_t squares = 0;
+        for (size_t i = 0; i < n_queries; ++i) squares += (uint64_t)query_length((uint32_t)i) * query_length((uint32_t)i);
+        stats.cells = (cells_total + squares) / 2;
+    }
+    stats.pairs_u16 = cells_u16, stats.pairs_s32 = cells_total - cells_u16;
+    engine.stats = stats;
+    return ok();
+}
+
+#pragma endregion
+
+} // namespace szb
+
+namespace szb {
+
+cudaError_t launch_wavefront(int family, int shape, int grid, size_t smem, cudaStream_t stream,
+                             KernelArgs const &args) {
+    switch (family) {
+    case FAM_LIN_SHIFT: return launch_family<FAM_LIN_SHIFT>(shape, grid, smem, stream, args);
+    case FAM_AFF_SHIFT: return launch_family<FAM_AFF_SHIFT>(shape, grid, smem, stream, args);
+    case FAM_SW_LIN: return launch_family<FAM_SW_LIN>(shape, grid, smem, stream, args);
+    case FAM_SW_AFF: return launch_family<FAM_SW_AFF>(shape, grid, smem, stream, args);
+    case FAM_S32_GLOBAL_LIN: return launch_family<FAM_S32_GLOBAL_LIN>(shape, grid, smem, stream, args);
+    case FAM_S32_GLOBAL_AFF: return launch_family<FAM_S32_GLOBAL_AFF>(shape, grid, smem, stream, args);
+    case FAM_S32_LOCAL_LIN: return launch_family<FAM_S32_LOCAL_LIN>(shape, grid, smem, stream, args);
+    default: return launch_family<FAM_S32_LOCAL_AFF>(shape, grid, smem, stream, args);
+    }
+}
+
+} // namespace szb
+
+#pragma region C ABI
+
+using szb::Engine;
+using szb::Failure;
+using szb::InputView;
+using szb::Scope;
+
+extern "C" {
+
+SZS_B200_API int szs_version_major(void) { return 5; } // tracks the reference ABI it drops in for: 5.1.2
+SZS_B200_API int szs_version_minor(void) { return 1; }
+SZS_B200_API int szs_version_patch(void) { return 2; }
+
+SZS_B200_API sz_capability_t szs_capabilities_comptime(void) {
+    return (sz_capability_t)(sz_cap_serial_k | sz_caps_cuda_k);
+}
+
+SZS_B200_API sz_capability_t szs_capabilities_runtime(void) {
+    // Like the reference (runtime.cuh:27-45): an unreachable GPU contributes no bits instead of an error.
+    int caps = sz_cap_serial_k;
+    if (szb::visible_device_count() > 0 && szb::device_sm_code(0) >= 100) caps |= sz_caps_cuda_k;
+    return (sz_capability_t)caps;
+}
+
+SZS_B200_API sz_capability_t szs_capabilities(void) {
+    return (sz_capability_t)(szs_capabilities_comptime() & szs_capabilities_runtime());
+}
+
+static void *unified_allocate(sz_size_t bytes, void *) { return szs_unified_alloc(bytes); }
+static void unified_free(void *pointer, sz_size_t bytes, void *) { szs_unified_free(pointer, bytes); }
+
+SZS_B200_API sz_status_t sz_memory_allocator_init_unified(sz_memory_allocator_t *alloc, char const **error_message) {
+    if (!alloc) return szb::report(szb::fail(sz_status_unknown_k, "Allocator pointer is null"), error_message);
+    alloc->allocate = &unified_allocate, alloc->free = &unified_free, alloc->handle = nullptr;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API void *szs_unified_alloc(sz_size_t size_bytes) {
+    void *pointer = nullptr;
+    if (cudaMallocManaged(&pointer, size_bytes ? size_bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return pointer;
+}
+
+SZS_B200_API void szs_unified_free(void *ptr, sz_size_t) {
+    if (ptr) cudaFree(ptr);
+}
+
+SZS_B200_API sz_status_t szs_device_scope_init_default(szs_device_scope_t *scope, char const **error_message) {
+    if (!scope) return szb::report(szb::fail(sz_status_unknown_k, "Scope pointer is null"), error_message);
+    auto *made = new (std::nothrow) Scope();
+    if (!made) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate device scope"), error_message);
+    made->kind = Scope::kDefault, made->cpu_cores = 1, made->gpu_device = 0;
+    *scope = made;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_device_scope_init_cpu_cores(sz_size_t cpu_cores, szs_device_scope_t *scope,
+                                                         char const **error_message) {
+    if (!scope) return szb::report(szb::fail(sz_status_unknown_k, "Scope pointer is null"), error_message);
+    // A one-core request folds back onto the default scope, as in the reference (runtime.cuh:93-94).
+    if (cpu_cores == 1) return szs_device_scope_init_default(scope, error_message);
+    auto *made = new (std::nothrow) Scope();
+    if (!made) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate device scope"), error_message);
+    made->kind = Scope::kCpu, made->cpu_cores = cpu_cores, made->gpu_device = -1;
+    *scope = made;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_device_scope_init_gpu_device(sz_size_t gpu_device, szs_device_scope_t *scope,
+                                                          char const **error_message) {
+    if (!scope) return szb::report(szb::fail(sz_status_unknown_k, "Scope pointer is null"), error_message);
+    if ((size_t)szb::visible_device_count() <= gpu_device)
+        return szb::report(szb::fail(sz_missing_gpu_k, "No such CUDA device"), error_message);
+    auto *made = new (std::nothrow) Scope();
+    if (!made) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate device scope"), error_message);
+    made->kind = Scope::kGpu, made->cpu_cores = 0, made->gpu_device = (int)gpu_device;
+    *scope = made;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_device_scope_get_cpu_cores(szs_device_scope_t scope, sz_size_t *cpu_cores,
+                                                        char const **error_message) {
+    if (!scope || !cpu_cores) return szb::report(szb::fail(sz_status_unknown_k, "Invalid null pointer argument"), error_message);
+    auto *typed = static_cast<Scope *>(scope);
+    if (typed->kind == Scope::kGpu) return szb::report(szb::fail(sz_status_unknown_k, "Device scope is GPU-only"), error_message);
+    *cpu_cores = typed->cpu_cores;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_device_scope_get_gpu_device(szs_device_scope_t scope, sz_size_t *gpu_device,
+                                                         char const **error_message) {
+    if (!scope || !gpu_device) return szb::report(szb::fail(sz_status_unknown_k, "Invalid null pointer argument"), error_message);
+    auto *typed = static_cast<Scope *>(scope);
+    if (typed->kind != Scope::kGpu) return szb::report(szb::fail(sz_status_unknown_k, "Device scope is CPU-only"), error_message);
+    *gpu_device = (sz_size_t)typed->gpu_device;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_device_scope_get_capabilities(szs_device_scope_t scope, sz_capability_t *capabilities,
+                                                           char const **error_message) {
+    if (!scope || !capabilities) return szb::report(szb::fail(sz_status_unknown_k, "Invalid null pointer argument"), error_message);
+    auto *typed = static_cast<Scope *>(scope);
+    int const system = szs_capabilities();
+    *capabilities = (sz_capability_t)(typed->kind == Scope::kGpu ? (system & sz_caps_cuda_k) : (system & sz_cap_serial_k));
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API void szs_device_scope_free(szs_device_scope_t scope) { delete static_cast<Scope *>(scope); }
+
+/* ---- Engines ---------------------------------------------------------------------------------------------------- */
+
+static sz_status_t make_engine(szb::Algorithm algorithm, void **handle, char const **error_message, Engine **made) {
+    if (!handle) return szb::report(szb::fail(sz_status_unknown_k, "Engine pointer is null"), error_message);
+    auto *engine = new (std::nothrow) Engine();
+    if (!engine) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate the engine"), error_message);
+    engine->algorithm = algorithm;
+    *handle = engine, *made = engine;
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_levenshtein_distances_init(sz_error_cost_t match, sz_error_cost_t mismatch,
+                                                        sz_error_cost_t open, sz_error_cost_t extend,
+                                                        sz_memory_allocator_t const *, sz_capability_t,
+                                                        szs_levenshtein_distances_t *engine,
+                                                        char const **error_message) {
+    Engine *made = nullptr;
+    sz_status_t status = make_engine(szb::Algorithm::kLevenshtein, engine, error_message, &made);
+    if (status != sz_success_k) return status;
+    made->match = match, made->mismatch = mismatch, made->open = open, made->extend = extend;
+    return status;
+}
+
+static sz_status_t init_weighted(szb::Algorithm algorithm, sz_u8_t const *byte_to_class,
+                                 sz_error_cost_t const *class_substitution_costs, sz_error_cost_t open,
+                                 sz_error_cost_t extend, void **engine, char const **error_message) {
+    if (!byte_to_class || !class_substitution_costs)
+        return szb::report(szb::fail(sz_status_unknown_k, "Substitution tables are null"), error_message);
+    Engine *made = nullptr;
+    sz_status_t status = make_engine(algorithm, engine, error_message, &made);
+    if (status != sz_success_k) return status;
+    std::memcpy(made->byte_to_class, byte_to_class, 256);
+    std::memcpy(made->costs, class_substitution_costs, 32 * 32);
+    made->open = open, made->extend = extend;
+    return status;
+}
+
+SZS_B200_API sz_status_t szs_needleman_wunsch_scores_init(sz_u8_t const *byte_to_class,
+                                                          sz_error_cost_t const *class_substitution_costs,
+                                                          sz_error_cost_t open, sz_error_cost_t extend,
+                                                          sz_memory_allocator_t const *, sz_capability_t,
+                                                          szs_needleman_wunsch_scores_t *engine,
+                                                          char const **error_message) {
+    return init_weighted(szb::Algorithm::kNeedlemanWunsch, byte_to_class, class_substitution_costs, open, extend,
+                         engine, error_message);
+}
+
+SZS_B200_API sz_status_t szs_smith_waterman_scores_init(sz_u8_t const *byte_to_class,
+                                                        sz_error_cost_t const *class_substitution_costs,
+                                                        sz_error_cost_t open, sz_error_cost_t extend,
+                                                        sz_memory_allocator_t const *, sz_capability_t,
+                                                        szs_smith_waterman_scores_t *engine,
+                                                        char const **error_message) {
+    return init_weighted(szb::Algorithm::kSmithWaterman, byte_to_class, class_substitution_costs, open, extend, engine,
+                         error_message);
+}
+
+static sz_status_t run(void *engine, szb::Algorithm expected, szs_device_scope_t device, InputView::Layout layout,
+                       void const *queries, void const *candidates, void *results, sz_size_t stride,
+                       char const **error_message) {
+    if (!engine || !device || !queries)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine, device scope and queries must not be null"), error_message);
+    auto *typed = static_cast<Engine *>(engine);
+    if (typed->algorithm != expected)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine handle belongs to another algorithm"), error_message);
+    InputView q {layout, queries}, c {layout, candidates};
+    Failure failure = szb::cross(*typed, *static_cast<Scope *>(device), q, c, results, stride, 0, 0, true);
+    return szb::report(failure, error_message);
+}
+
+#define SZB_DEFINE_CALLS(name, algorithm, result_type)                                                                 \
+    SZS_B200_API sz_status_t name(void *engine, szs_device_scope_t device, sz_sequence_t const *queries,                \
+                                  sz_sequence_t const *candidates, result_type *results, sz_size_t stride,             \
+                                  char const **error_message) {                                                        \
+        return run(engine, algorithm, device, InputView::kSequence, queries, candidates, results, stride,              \
+                   error_message);                                                                                     \
+    }                                                                                                                  \
+    SZS_B200_API sz_status_t name##_u32tape(void *engine, szs_device_scope_t device,                                    \
+                                            sz_sequence_u32tape_t const *queries,                                      \
+                                            sz_sequence_u32tape_t const *candidates, result_type *results,             \
+                                            sz_size_t stride, char const **error_message) {                            \
+        return run(engine, algorithm, device, InputView::kTape32, queries, candidates, results, stride,                \
+                   error_message);                                                                                     \
+    }                                                                                                                  \
+    SZS_B200_API sz_status_t name##_u64tape(void *engine, szs_device_scope_t device,                                    \
+                                            sz_sequence_u64tape_t const *queries,                                      \
+                                            sz_sequence_u64tape_t const *candidates, result_type *results,             \
+                                            sz_size_t stride, char const **error_message) {                            \
+        return run(engine, algorithm, device, InputView::kTape64, queries, candidates, results, stride,                \
+                   error_message);                                                                                     \
+    }                                                                                                                  \
+    SZS_B200_API void name##_free(void *engine) { delete static_cast<Engine *>(engine); }
+
+SZB_DEFINE_CALLS(szs_levenshtein_distances, szb::Algorithm::kLevenshtein, sz_size_t)
+SZB_DEFINE_CALLS(szs_needleman_wunsch_scores, szb::Algorithm::kNeedlemanWunsch, sz_ssize_t)
+SZB_DEFINE_CALLS(szs_smith_waterman_scores, szb::Algorithm::kSmithWaterman, sz_ssize_t)
+
+/* ---- Out-of-scope families: present so that bindings resolve, refusing loudly (no CPU fallback). ---------------- */
+
+static sz_status_t out_of_scope(char const **error_message) {
+    return szb::report(szb::fail(sz_missing_gpu_k, "Not part of the stringzillas_b200 hot path"), error_message);
+}
+
+SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_init(sz_error_cost_t, sz_error_cost_t, sz_error_cost_t,
+                                                             sz_error_cost_t, sz_memory_allocator_t const *,
+                                                             sz_capability_t, szs_levenshtein_distances_utf8_t *,
+                                                             char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API sz_status_t szs_levenshtein_distances_utf8(szs_levenshtein_distances_utf8_t, szs_device_scope_t,
+                                                        sz_sequence_t const *, sz_sequence_t const *, sz_size_t *,
+                                                        sz_size_t, char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_u32tape(szs_levenshtein_distances_utf8_t, szs_device_scope_t,
+                                                                sz_sequence_u32tape_t const *,
+                                                                sz_sequence_u32tape_t const *, sz_size_t *, sz_size_t,
+                                                                char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_u64tape(szs_levenshtein_distances_utf8_t, szs_device_scope_t,
+                                                                sz_sequence_u64tape_t const *,
+                                                                sz_sequence_u64tape_t const *, sz_size_t *, sz_size_t,
+                                                                char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API void szs_levenshtein_distances_utf8_free(szs_levenshtein_distances_utf8_t) {}
+
+SZS_B200_API sz_status_t szs_fingerprints_init(sz_size_t, sz_size_t, sz_size_t const *, sz_size_t, sz_u64_t,
+                                               sz_memory_allocator_t const *, sz_capability_t, szs_fingerprints_t *,
+                                               char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API sz_status_t szs_fingerprints_sequence(szs_fingerprints_t, szs_device_scope_t, sz_sequence_t const *,
+                                                   sz_u32_t *, sz_size_t, sz_u32_t *, sz_size_t,
+                                                   char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API sz_status_t szs_fingerprints_u32tape(szs_fingerprints_t, szs_device_scope_t,
+                                                  sz_sequence_u32tape_t const *, sz_u32_t *, sz_size_t, sz_u32_t *,
+                                                  sz_size_t, char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API sz_status_t szs_fingerprints_u64tape(szs_fingerprints_t, szs_device_scope_t,
+                                                  sz_sequence_u64tape_t const *, sz_u32_t *, sz_size_t, sz_u32_t *,
+                                                  sz_size_t, char const **error_message) {
+    return out_of_scope(error_message);
+}
+SZS_B200_API void szs_fingerprints_free(szs_fingerprints_t) {}
+
+/* ---- B200 additions ---------------------------------------------------------------------------------------------- */
+
+SZS_B200_API sz_status_t szs_b200_last_call_stats(void const *engine, szs_b200_call_stats_t *stats) {
+    if (!engine || !stats) return sz_status_unknown_k;
+    *stats = static_cast<Engine const *>(engine)->stats;
+    return sz_success_k;
+}
+
+SZS_B200_API sz_status_t szs_b200_scores_u64tape_rows(int family, void *engine, szs_device_scope_t device,
+                                                      sz_sequence_u64tape_t const *queries,
+                                                      sz_sequence_u64tape_t const *candidates, sz_size_t row_begin,
+                                                      sz_size_t row_end, void *results, sz_size_t results_row_stride,
+                                                      char const **error_message) {
+    if (!engine || !device || !queries)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine, device scope and queries must not be null"), error_message);
+    auto *typed = static_cast<Engine *>(engine);
+    if ((int)typed->algorithm != family)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine handle belongs to another algorithm"), error_message);
+    InputView q {InputView::kTape64, queries}, c {InputView::kTape64, candidates};
+    Failure failure = szb::cross(*typed, *static_cast<Scope *>(device), q, c, results, results_row_stride, row_begin,
+                                 row_end, false);
+    return szb::report(failure, error_message);
+}
+
+} // extern "C"
+
+#pragma endregion

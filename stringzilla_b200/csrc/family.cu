@@ -1,0 +1,41 @@
+/**
+ *  @file family.cu
+ *  @brief One translation unit per recurrence family: compile with -DSZB_FAMILY=<0..7>.
+ */
+#include "launch.cuh"
+
+#ifndef SZB_FAMILY
+#error "compile with -DSZB_FAMILY=<family index>"
+#endif
+
+namespace szb {
+
+template <int FAM, int SHAPE>
+static cudaError_t launch_shape(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
+    constexpr int K = kShapes[SHAPE].k, G = kShapes[SHAPE].g;
+    auto kernel = wavefront_kernel<FAM, K, G>;
+    // Opt in to the large dynamic shared-memory carve-out once per kernel and device.
+    static bool configured[64] = {false};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (device < 64 && !configured[device]) {
+        cudaError_t status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (status != cudaSuccess) return status;
+        configured[device] = true;
+    }
+    kernel<<<grid, kThreads, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+template <>
+cudaError_t launch_family<SZB_FAMILY>(int shape, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
+    switch (shape) {
+    case 0: return launch_shape<SZB_FAMILY, 0>(grid, smem, stream, args);
+    case 1: return launch_shape<SZB_FAMILY, 1>(grid, smem, stream, args);
+    case 2: return launch_shape<SZB_FAMILY, 2>(grid, smem, stream, args);
+    case 3: return launch_shape<SZB_FAMILY, 3>(grid, smem, stream, args);
+    default: return launch_shape<SZB_FAMILY, 4>(grid, smem, stream, args);
+    }
+}
+
+} // namespace szb

@@ -1,0 +1,468 @@
+/**
+ *  @file kernels.cuh
+ *  @brief sm_100a device code of the batched string-similarity hot path: one skewed register wavefront per
+ *         (query, candidate-pair), DPX min/max-fused recurrences on packed 2 x u16 cells.
+ *
+ *  Replaces (does not port) the reference's anti-diagonal shared-memory warp kernels and their Hopper DPX cell
+ *  functors: /root/reference/include/stringzillas/similarities/cuda.cuh:1246-1626 and hopper.cuh:45-617.
+ *
+ *  Data flow of one launch
+ *  -----------------------
+ *  A "slot" is a pair of candidates (c0, c1) of similar length whose DP cells travel together as the low / high
+ *  16-bit halves of one 32-bit register, so that every DPX instruction (VIMNMX3.U16x2 / VIADDMNMX.U16x2) retires two
+ *  independent cells. A "job" is a slot x a block of queries. A persistent CTA pulls jobs from an atomic counter;
+ *  for each job (and each 1024-column pass of long candidates) it
+ *    1. builds the slot's *substitution profile* in shared memory: prof[a][j] = packed (e(a, c0[j]), e(a, c1[j]))
+ *       for every row class `a` — so the inner loop never compares characters or touches the 32x32 cost table,
+ *    2. lets each warp (or sub-warp group of G lanes) sweep one query over the profile: lane `l` owns K consecutive
+ *       DP columns in registers and processes DP row `s - l` at step `s` (a skewed wavefront); the only inter-lane
+ *       traffic is one `__shfl_up` of the strip's last cell per step (two for affine gaps).
+ *  Profile rows are vector-interleaved ([vector v][lane l] -> 16 bytes) so that the LDS.128 of the 8 lanes of a
+ *  quarter-warp covers all 32 banks whatever rows (classes) the lanes are reading: conflict-free by construction.
+ *
+ *  Recurrences (all MAXIMISING; Levenshtein runs with negated costs and a negated result)
+ *  --------------------------------------------------------------------------------------
+ *  FAM_LIN_SHIFT  (Levenshtein & Needleman-Wunsch, linear gaps): u(i,j) = H(i,j) - (i+j)*g turns the gap term into
+ *      a plain max:  u = max3(u_diag + e, u_up, u_left),  e = max(S - 2g, 0)  (S < 2g can never win against two
+ *      gaps, so the clamp is exact). One IADD (FMA-pipe IMAD.IADD) + one VIMNMX3.U16x2 per packed cell pair, all
+ *      boundaries are zero. Follows the semantics of reference test/similarities.cuh:47-100.
+ *  FAM_AFF_SHIFT  (Levenshtein & NW, affine gaps): shifted by the extension cost and offset by O = 4*go,
+ *      go = extend - open >= 0:  F = max(w_up - go, F_up), E = max(w_left - go, E_left), w = max3(w_diag + e, E, F),
+ *      e = max(S, 2*open) - 2*extend.  Reference test/similarities.cuh:136-228 (Gotoh with the finite
+ *      "discard" seeds, equivalent to -inf seeds whenever extend <= 0, which the host checks).
+ *  FAM_SW_LIN / FAM_SW_AFF (Smith-Waterman): unshifted, cells biased by B so every half stays non-negative and a
+ *      plain 32-bit add of an arithmetically packed (possibly negative) profile entry is exact per half.
+ *      Reference test/similarities.cuh:103-133, 234-280.
+ *  FAM_S32_*      one candidate per register, signed 32-bit cells, literal baseline recurrences with DPX s32 ops;
+ *      serves pairs whose scores do not fit 16 bits, unusual cost signs, and Levenshtein over alphabets of more than
+ *      31 distinct bytes (compare mode: the substitution is a byte comparison instead of a profile lookup).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace szb {
+
+enum Family : int {
+    FAM_LIN_SHIFT = 0,
+    FAM_AFF_SHIFT = 1,
+    FAM_SW_LIN = 2,
+    FAM_SW_AFF = 3,
+    FAM_S32_GLOBAL_LIN = 4,
+    FAM_S32_GLOBAL_AFF = 5,
+    FAM_S32_LOCAL_LIN = 6,
+    FAM_S32_LOCAL_AFF = 7,
+};
+
+constexpr int kThreads = 512;                  ///< 16 warps per persistent CTA, one CTA per SM
+constexpr uint32_t kNoCandidate = 0xFFFFFFFFu; ///< `CandSlot::c1` of an unpaired slot
+
+/** Scoring model of one engine, in the kernel's maximising convention. Lives in device memory. */
+struct Scoring {
+    int8_t sub[32 * 32]; ///< sub[a * 32 + b]: class(query byte) = a (row), class(candidate byte) = b (column)
+    int32_t n_classes;   ///< profile rows actually in use (max class id + 1)
+    int32_t open;        ///< cost ADDED for the first character of a gap (linear gaps: open == extend)
+    int32_t extend;      ///< cost ADDED for every further character of a gap
+    int32_t negate;      ///< 1 for Levenshtein: reported distance = -H
+    int32_t bias;        ///< FAM_AFF_SHIFT: O = 4*go; FAM_SW_*: B; else 0
+    int32_t compare;     ///< FAM_S32_*: 1 = strings hold raw bytes, substitution = (a == b) ? match : mismatch
+    int32_t match;       ///< compare mode, maximising convention
+    int32_t mismatch;    ///< compare mode, maximising convention
+};
+
+/** A pair of candidates travelling in the two 16-bit halves of each register (or a single one for FAM_S32_*). */
+struct CandSlot {
+    uint32_t c0, c1;     ///< candidate indices; c1 == kNoCandidate when unpaired
+    uint32_t len0, len1; ///< lengths in bytes; len1 == 0 when unpaired
+};
+
+/** A slot scored against the queries `q_order[q_begin .. q_end)`. */
+struct Job {
+    uint32_t slot, q_begin, q_end, scratch_words; ///< scratch_words: multi-pass boundary storage this job needs
+};
+
+struct KernelArgs {
+    uint8_t const *q_cls;  ///< class-mapped (or raw, in compare mode) query bytes
+    uint32_t const *q_off; ///< Q+1 offsets into q_cls
+    uint8_t const *c_cls;
+    uint32_t const *c_off;
+    uint32_t const *q_order; ///< query indices, longest first
+    CandSlot const *slots;
+    Job const *jobs;
+    uint32_t n_jobs;
+    uint32_t *job_counter;
+    Scoring const *scoring;
+    int64_t *results;        ///< results[(q - row_base) * stride + c]
+    uint64_t stride;
+    uint32_t row_base;
+    uint32_t *scratch;       ///< per-CTA multi-pass boundary storage
+    uint64_t scratch_words_per_cta;
+};
+
+__device__ __forceinline__ uint32_t pack_arith(int lo, int hi) { return (uint32_t)(hi * 65536 + lo); }
+__device__ __forceinline__ uint32_t pack_bits(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+
+template <int FAM>
+struct family_traits {
+    static constexpr bool packed = FAM <= FAM_SW_AFF;
+    static constexpr bool affine =
+        FAM == FAM_AFF_SHIFT || FAM == FAM_SW_AFF || FAM == FAM_S32_GLOBAL_AFF || FAM == FAM_S32_LOCAL_AFF;
+    static constexpr bool local =
+        FAM == FAM_SW_LIN || FAM == FAM_SW_AFF || FAM == FAM_S32_LOCAL_LIN || FAM == FAM_S32_LOCAL_AFF;
+};
+
+/** Substitution term stored in the profile for row class `a` against candidate class `b` (or padding). */
+template <int FAM>
+__device__ __forceinline__ int profile_term(int8_t const *sub, int a, int b, bool valid, int open, int extend,
+                                            int bias) {
+    int const s = valid ? (int)sub[a * 32 + b] : 0;
+    if constexpr (FAM == FAM_LIN_SHIFT) { return valid ? max(s - 2 * open, 0) : 0; }
+    else if constexpr (FAM == FAM_AFF_SHIFT) { return valid ? max(s, 2 * open) - 2 * extend : 2 * (open - extend); }
+    else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) { return valid ? s : -bias; }
+    else { return valid ? s : -(1 << 28); }
+}
+
+/** Score of aligning `len` characters against nothing: serial.hpp:165-177 of the reference. */
+template <int FAM>
+__device__ __forceinline__ int64_t degenerate_score(int64_t len, int open, int extend) {
+    if constexpr (family_traits<FAM>::local) return 0;
+    else if constexpr (family_traits<FAM>::affine) return len == 0 ? 0 : (int64_t)open + (int64_t)extend * (len - 1);
+    else return (int64_t)open * len;
+}
+
+/**
+ *  @brief One persistent CTA: pulls jobs, builds profiles, sweeps queries.
+ *  @tparam FAM recurrence family, @tparam K DP columns per lane, @tparam G lanes per query (wavefront width).
+ */
+template <int FAM, int K, int G>
+__global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const args) {
+    using traits = family_traits<FAM>;
+    constexpr bool packed = traits::packed, affine = traits::affine, local = traits::local;
+    constexpr int COLS = K * G;       // DP columns covered by one pass
+    constexpr int GROUPS = 32 / G;    // queries swept by one warp at a time
+    constexpr int VECS = K / 4;       // LDS.128 per lane per row
+    static_assert(K % 4 == 0 && G >= 8 && 32 % G == 0, "unsupported strip shape");
+
+    extern __shared__ __align__(16) uint32_t smem[];
+    Scoring const *const sc_global = args.scoring;
+    int const n_classes = sc_global->n_classes;
+    bool const compare = !packed && sc_global->compare != 0;
+    uint32_t *const prof = smem; // [n_classes][COLS], vector-interleaved; absent in compare mode
+    int8_t *const sub = (int8_t *)(smem + (compare ? 0 : (size_t)n_classes * COLS)); // 1024 B
+    uint32_t *const ctl = (uint32_t *)(sub + 1024);                                  // [0] job index, [1] next batch
+
+    int const open = sc_global->open, extend = sc_global->extend, bias = sc_global->bias;
+    int const negate = sc_global->negate;
+    int const cmp_match = sc_global->match, cmp_mismatch = sc_global->mismatch;
+    int const go = extend - open;
+
+    for (int i = threadIdx.x; i < 256; i += kThreads) ((uint32_t *)sub)[i] = ((uint32_t const *)sc_global->sub)[i];
+
+    int const lane = threadIdx.x & 31;
+    int const gl = lane % G, gi = lane / G;
+
+    // Constants of the recurrences, packed per half where the DPX instruction needs them bitwise.
+    uint32_t const k_neg_go = pack_bits(-go);          // FAM_AFF_SHIFT: "- go" for VIADDMNMX
+    uint32_t const k_bias = pack_bits(bias);           // FAM_SW_*: the zero floor in biased units
+    uint32_t const k_gap_bits = pack_bits(open);       // FAM_SW_*: "+ open" for VIADDMNMX
+    uint32_t const k_gap_arith = pack_arith(open, open);       // FAM_SW_LIN: "+ g" through a plain add
+    uint32_t const k_ext_arith = pack_arith(extend, extend);   // FAM_SW_AFF: "+ extend" through a plain add
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ctl[0] = atomicAdd(args.job_counter, 1u);
+            ctl[1] = 0;
+        }
+        __syncthreads();
+        uint32_t const job_index = ctl[0];
+        if (job_index >= args.n_jobs) break;
+        Job const job = args.jobs[job_index];
+        CandSlot const slot = args.slots[job.slot];
+        uint32_t const longest = max(slot.len0, slot.len1);
+        int const passes = longest == 0 ? 1 : (int)((longest + COLS - 1) / COLS);
+        uint8_t const *const c0_ptr = args.c_cls + args.c_off[slot.c0];
+        uint8_t const *const c1_ptr = slot.c1 != kNoCandidate ? args.c_cls + args.c_off[slot.c1] : c0_ptr;
+        uint32_t *const scratch = args.scratch + (size_t)blockIdx.x * args.scratch_words_per_cta;
+        uint32_t const n_queries = job.q_end - job.q_begin;
+        uint32_t const n_batches = (n_queries + GROUPS - 1) / GROUPS;
+
+        for (int pass = 0; pass < passes; ++pass) {
+            uint32_t const pass_base = (uint32_t)pass * COLS;
+            __syncthreads(); // every warp is done with the previous profile and batch counter
+            if (threadIdx.x == 0) ctl[1] = 0;
+
+            // 1. Build the substitution profile of this slot's columns [pass_base, pass_base + COLS).
+            if (!compare) {
+                for (int idx = threadIdx.x; idx < n_classes * COLS; idx += kThreads) {
+                    int const a = idx / COLS, j = idx % COLS;
+                    uint32_t const col = pass_base + j;
+                    bool const v0 = col < slot.len0, v1 = col < slot.len1;
+                    int const b0 = v0 ? c0_ptr[col] : 0, b1 = v1 ? c1_ptr[col] : 0;
+                    int const e0 = profile_term<FAM>(sub, a, b0, v0, open, extend, bias);
+                    int const e1 = profile_term<FAM>(sub, a, b1, v1, open, extend, bias);
+                    int const strip = j / K, k = j % K;
+                    int const word = ((k / 4) * G + strip) * 4 + (k % 4);
+                    prof[a * COLS + word] = packed ? pack_arith(e0, e1) : (uint32_t)e0;
+                }
+            }
+            __syncthreads();
+
+            // 2. Warps pull batches of GROUPS queries and sweep them over the profile.
+            for (;;) {
+                uint32_t batch = 0;
+                if (lane == 0) batch = atomicAdd(&ctl[1], 1u);
+                batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
+                if (batch >= n_batches) break;
+
+                uint32_t const q_pos = batch * GROUPS + gi;
+                bool const q_valid = q_pos < n_queries;
+                uint32_t const q = q_valid ? args.q_order[job.q_begin + q_pos] : 0;
+                uint32_t const q_begin_off = q_valid ? args.q_off[q] : 0;
+                int const m = q_valid ? (int)(args.q_off[q + 1] - q_begin_off) : 0;
+                uint8_t const *const q_ptr = args.q_cls + q_begin_off;
+
+                // Multi-pass boundary storage: the last DP column of the previous pass, one row-slot per query row.
+                // Queries of a job are sorted longest-first, so the job's first query bounds every row count.
+                uint32_t *bnd = nullptr;
+                if (passes > 1) {
+                    uint32_t const first = args.q_order[job.q_begin];
+                    uint32_t const rows = args.q_off[first + 1] - args.q_off[first] + 1;
+                    bnd = scratch + (size_t)q_pos * rows * (affine ? 2 : 1);
+                }
+
+                int const cbase = (int)pass_base + gl * K; // DP column left of this lane's strip
+                bool const first_strip = pass == 0 && gl == 0;
+
+                // Top boundary: DP row 0 of the strip, and the seeds of the gap tracks.
+                uint32_t h[K], f[affine ? K : 1];
+                uint32_t cb[(!packed) ? VECS : 1]; // compare mode: the strip's raw candidate bytes
+                uint32_t diag_in, w_out = 0, e_out = 0, best = 0;
+                if constexpr (FAM == FAM_LIN_SHIFT) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) h[k] = 0;
+                    diag_in = 0;
+                }
+                else if constexpr (FAM == FAM_AFF_SHIFT) {
+                    uint32_t const top = pack_bits(bias - go);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) h[k] = top, f[k] = 0;
+                    diag_in = first_strip ? pack_bits(bias) : top;
+                }
+                else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) h[k] = k_bias;
+                    if constexpr (affine) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) f[k] = pack_bits(bias + open + extend);
+                    }
+                    diag_in = k_bias;
+                    best = k_bias;
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        int const top = (int)degenerate_score<FAM>(cbase + 1 + k, open, extend);
+                        h[k] = (uint32_t)top;
+                        if constexpr (affine) f[k] = (uint32_t)(top + open + extend);
+                    }
+                    diag_in = (uint32_t)(int)degenerate_score<FAM>(cbase, open, extend);
+                    if (compare) {
+#pragma unroll
+                        for (int v = 0; v < VECS; ++v) {
+                            uint32_t word = 0;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint32_t const col = (uint32_t)cbase + v * 4 + i;
+                                uint32_t const byte = col < slot.len0 ? c0_ptr[col] : 0x100u; // never equal
+                                word |= (byte & 0xFFu) << (8 * i);
+                                // Padding columns compare against a real byte value; their cells are never read.
+                            }
+                            cb[v] = word;
+                        }
+                    }
+                }
+
+                // Number of steps: the longest query of the warp's groups plus the pipeline fill.
+                int steps = m > 0 ? m + G - 1 : 0;
+#pragma unroll
+                for (int offset = 16; offset >= G; offset >>= 1)
+                    steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, offset));
+
+                uint32_t a_next = (gl == 0 && m > 0) ? q_ptr[0] : 0;
+                uint32_t bw_next = 0, be_next = 0;
+                if (pass > 0 && gl == 0 && m > 0) {
+                    bw_next = bnd[affine ? 2 : 1];
+                    if constexpr (affine) be_next = bnd[3];
+                }
+
+                for (int s = 0; s < steps; ++s) {
+                    int const r = s - gl + 1; // DP row processed in this step
+                    bool const valid = r >= 1 && r <= m;
+
+                    // Strip's left neighbour: the last cell of the lane to the left, one step ago.
+                    uint32_t w_in = __shfl_up_sync(0xFFFFFFFFu, w_out, 1, G);
+                    uint32_t e_in = 0;
+                    if constexpr (affine) e_in = __shfl_up_sync(0xFFFFFFFFu, e_out, 1, G);
+                    if (gl == 0) {
+                        if (pass == 0) {
+                            if constexpr (FAM == FAM_LIN_SHIFT) w_in = 0;
+                            else if constexpr (FAM == FAM_AFF_SHIFT) w_in = pack_bits(bias - go), e_in = 0;
+                            else if constexpr (FAM == FAM_SW_LIN) w_in = k_bias;
+                            else if constexpr (FAM == FAM_SW_AFF) w_in = k_bias, e_in = pack_bits(bias + open + extend);
+                            else {
+                                w_in = (uint32_t)(int)degenerate_score<FAM>(r, open, extend);
+                                if constexpr (affine) e_in = w_in + (uint32_t)(open + extend);
+                            }
+                        }
+                        else { w_in = bw_next, e_in = be_next; }
+                    }
+
+                    uint32_t const a = a_next;
+                    {   // Prefetch the next row's class and (multi-pass) boundary cell.
+                        int const next = s + 1 - gl;
+                        bool const has_next = next >= 0 && next < m;
+                        a_next = has_next ? q_ptr[next] : 0;
+                        if (pass > 0 && gl == 0 && has_next) {
+                            bw_next = bnd[(next + 1) * (affine ? 2 : 1)];
+                            if constexpr (affine) be_next = bnd[(next + 1) * 2 + 1];
+                        }
+                    }
+
+                    if (valid) {
+                        uint32_t d = diag_in, l = w_in, e = e_in;
+                        uint4 const *const prow = (uint4 const *)(prof + (size_t)a * COLS) + gl;
+                        int const a_int = (int)a;
+#pragma unroll
+                        for (int v = 0; v < VECS; ++v) {
+                            uint32_t p[4];
+                            if (!compare) {
+                                uint4 const pv = prow[v * G];
+                                p[0] = pv.x, p[1] = pv.y, p[2] = pv.z, p[3] = pv.w;
+                            }
+                            else {
+                                if constexpr (!packed) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        p[i] = (uint32_t)(((cb[v] >> (8 * i)) & 0xFFu) == (uint32_t)a_int ? cmp_match
+                                                                                                          : cmp_mismatch);
+                                }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                int const k = v * 4 + i;
+                                if constexpr (FAM == FAM_LIN_SHIFT) {
+                                    uint32_t const t = d + p[i];
+                                    d = h[k];
+                                    l = h[k] = __vimax3_u16x2(t, h[k], l);
+                                }
+                                else if constexpr (FAM == FAM_AFF_SHIFT) {
+                                    uint32_t const t = d + p[i];
+                                    d = h[k];
+                                    f[k] = __viaddmax_u16x2(h[k], k_neg_go, f[k]);
+                                    e = __viaddmax_u16x2(l, k_neg_go, e);
+                                    l = h[k] = __vimax3_u16x2(t, f[k], e);
+                                }
+                                else if constexpr (FAM == FAM_SW_LIN) {
+                                    uint32_t const t = d + p[i];
+                                    uint32_t const up_gap = h[k] + k_gap_arith;
+                                    d = h[k];
+                                    uint32_t const x = __vimax3_u16x2(t, up_gap, k_bias);
+                                    l = h[k] = __viaddmax_u16x2(l, k_gap_bits, x);
+                                    if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
+                                }
+                                else if constexpr (FAM == FAM_SW_AFF) {
+                                    uint32_t const t = d + p[i];
+                                    d = h[k];
+                                    f[k] = __viaddmax_u16x2(h[k], k_gap_bits, f[k] + k_ext_arith);
+                                    e = __viaddmax_u16x2(l, k_gap_bits, e + k_ext_arith);
+                                    uint32_t const x = __vimax3_u16x2(t, f[k], k_bias);
+                                    l = h[k] = __vmaxu2(x, e);
+                                    if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
+                                }
+                                else { // signed 32-bit cells, literal recurrences
+                                    int const t = (int)d + (int)p[i];
+                                    d = h[k];
+                                    int score;
+                                    if constexpr (affine) {
+                                        int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
+                                        int const ins = __viaddmax_s32((int)l, open, (int)e + extend);
+                                        f[k] = (uint32_t)del, e = (uint32_t)ins;
+                                        score = __vimax3_s32(t, del, ins);
+                                    }
+                                    else { score = __viaddmax_s32(max((int)h[k], (int)l), open, t); }
+                                    if constexpr (local) {
+                                        score = max(score, 0);
+                                        best = (uint32_t)max((int)best, score);
+                                    }
+                                    l = h[k] = (uint32_t)score;
+                                }
+                            }
+                        }
+                        diag_in = w_in;
+                        w_out = l, e_out = e;
+                        if (gl == G - 1 && pass + 1 < passes) {
+                            bnd[r * (affine ? 2 : 1)] = l;
+                            if constexpr (affine) bnd[r * 2 + 1] = e;
+                        }
+                    }
+                }
+
+                // 3. Harvest: the cell (m, n) of each half for global alignments, the running maximum for local ones.
+#pragma unroll
+                for (int half = 0; half < (packed ? 2 : 1); ++half) {
+                    uint32_t const cand = half == 0 ? slot.c0 : slot.c1;
+                    if (cand == kNoCandidate) continue; // uniform across the CTA
+                    int const n = (int)(half == 0 ? slot.len0 : slot.len1);
+                    int64_t *const out = args.results + (uint64_t)(q - args.row_base) * args.stride + cand;
+
+                    if constexpr (!local) {
+                        if (m == 0 || n == 0) {
+                            if (pass == 0 && gl == 0 && q_valid) {
+                                int64_t const score = degenerate_score<FAM>(m == 0 ? n : m, open, extend);
+                                *out = negate ? -score : score;
+                            }
+                            continue;
+                        }
+                        if ((n - 1) / COLS != pass) continue; // uniform across the CTA
+                        int const lane_star = ((n - 1) % COLS) / K, k_star = (n - 1) % K;
+                        uint32_t cell = 0;
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            if (k == k_star) cell = h[k];
+                        if (gl == lane_star && q_valid) {
+                            int64_t score;
+                            if constexpr (FAM == FAM_LIN_SHIFT)
+                                score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) + (int64_t)(m + n) * open;
+                            else if constexpr (FAM == FAM_AFF_SHIFT)
+                                score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) - bias + (int64_t)(m + n) * extend;
+                            else score = (int64_t)(int)cell;
+                            *out = negate ? -score : score;
+                        }
+                    }
+                    else {
+                        // Reduce the running maximum over the group's lanes.
+                        uint32_t group_best = best;
+#pragma unroll
+                        for (int offset = G / 2; offset >= 1; offset >>= 1) {
+                            uint32_t const other = __shfl_xor_sync(0xFFFFFFFFu, group_best, offset);
+                            if constexpr (packed) group_best = __vmaxu2(group_best, other);
+                            else group_best = (uint32_t)max((int)group_best, (int)other);
+                        }
+                        int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias
+                                               : (int64_t)(int)group_best;
+                        if (gl == 0 && q_valid) {
+                            // Later passes of a long candidate fold into the cell written by pass 0 (same CTA,
+                            // ordered by the pass barrier).
+                            if (m == 0 || n == 0) score = 0;
+                            if (pass == 0) *out = score;
+                            else if (score > *out) *out = score;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+} // namespace szb

@@ -1,0 +1,247 @@
+"""GPU suite: the CUDA path, called through the C ABI, must equal the oracle bit for bit (all three families are exact
+integer DP — the reference's own tests assert equality, test/similarities.cuh:543-545, 676-680, 1229-1232)."""
+
+import ctypes as ct
+import json
+
+import numpy as np
+import pytest
+
+import stringzilla_b200 as szb
+from stringzilla_b200 import _abi, scoring
+from tests import support
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.loads((support.GOLDEN_DIR / "reference_vectors.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def scope():
+    return szb.DeviceScope(gpu_device=0)
+
+
+def engine_for(kind, params):
+    if kind == "levenshtein":
+        return szb.LevenshteinDistances(*params["costs"])
+    engine_type = szb.NeedlemanWunschScores if kind == "needleman_wunsch" else szb.SmithWatermanScores
+    return engine_type(np.array(params["byte_to_class"], dtype=np.uint8),
+                       np.array(params["costs"], dtype=np.int8).reshape(32, 32),
+                       open=params["open"], extend=params["extend"])  # fmt: skip
+
+
+@pytest.mark.parametrize("case", GOLDEN["cases"], ids=[c["name"] for c in GOLDEN["cases"]])
+def test_golden_vectors_of_the_reference(case, scope):
+    queries = [bytes.fromhex(q) for q in case["queries"]]
+    candidates = None if case["candidates"] is None else [bytes.fromhex(c) for c in case["candidates"]]
+    got = engine_for(case["kind"], case["params"])(queries, candidates, device=scope)
+    assert np.array_equal(got.astype(np.int64), np.array(case["matrix"], dtype=np.int64))
+
+
+def test_known_answer_levenshtein_vectors(scope):
+    engine = szb.LevenshteinDistances()
+    for first, second, distance in GOLDEN["known_levenshtein"]:
+        assert int(engine([first.encode()], [second.encode()], device=scope)[0, 0]) == distance, (first, second)
+    firsts = [a.encode() for a, _, _ in GOLDEN["known_levenshtein"]]
+    seconds = [b.encode() for _, b, _ in GOLDEN["known_levenshtein"]]
+    batch = engine(firsts, seconds, device=scope)
+    assert [int(batch[i, i]) for i in range(len(firsts))] == [d for _, _, d in GOLDEN["known_levenshtein"]]
+
+
+# Length bands chosen to land in every strip shape: (8,8) <=64, (16,8) <=128, (32,8) <=256, (32,16) <=512, (32,32)
+# single pass <=1024 and multi-pass beyond.
+LENGTH_BANDS = [(1, 64), (50, 128), (100, 256), (200, 512), (400, 1024), (900, 2600)]
+LEVENSHTEIN_COSTS = [(0, 1, 1, 1), (1, 3, 3, 3), (1, 3, 4, 2), (0, 2, 5, 1)]
+
+
+@pytest.mark.parametrize("band", LENGTH_BANDS, ids=[f"len{a}-{b}" for a, b in LENGTH_BANDS])
+@pytest.mark.parametrize("costs", LEVENSHTEIN_COSTS, ids=["unit", "weird_linear", "weird_affine", "affine"])
+def test_levenshtein_random_cross_products(band, costs, scope):
+    rng = np.random.default_rng(hash((band, costs)) & 0xFFFF)
+    n = 23 if band[1] <= 1024 else 7
+    queries = support.random_strings(rng, n, band[0], band[1], support.DNA)
+    candidates = support.mutated_copies(rng, queries[: n - 4], 0.15, support.DNA) + support.random_strings(
+        rng, 5, band[0], band[1], support.DNA)
+    got = szb.LevenshteinDistances(*costs)(queries, candidates, device=scope)
+    assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs))
+
+
+@pytest.mark.parametrize("band", LENGTH_BANDS, ids=[f"len{a}-{b}" for a, b in LENGTH_BANDS])
+@pytest.mark.parametrize("gaps", [(-4, -4), (-4, -1), (-11, -1)], ids=["linear", "affine", "affine_wide"])
+@pytest.mark.parametrize("local", [False, True], ids=["needleman_wunsch", "smith_waterman"])
+def test_weighted_random_cross_products(band, gaps, local, scope):
+    rng = np.random.default_rng(hash((band, gaps, local)) & 0xFFFF)
+    byte_to_class, costs = scoring.blosum62()
+    n = 19 if band[1] <= 1024 else 6
+    queries = support.random_strings(rng, n, band[0], band[1], support.PROTEIN)
+    candidates = support.mutated_copies(rng, queries[: n - 3], 0.25, support.PROTEIN) + support.random_strings(
+        rng, 4, band[0], band[1], support.PROTEIN)
+    engine_type = szb.SmithWatermanScores if local else szb.NeedlemanWunschScores
+    got = engine_type(byte_to_class, costs, open=gaps[0], extend=gaps[1])(queries, candidates, device=scope)
+    assert np.array_equal(got, support.oracle_weighted(queries, candidates, byte_to_class, costs, *gaps, local))
+
+
+def test_mixed_lengths_one_call(scope):
+    """Log-uniform lengths 1..3000 in one tile: every strip shape, both tiers and multi-pass slots in one launch set."""
+    rng = np.random.default_rng(11)
+    lengths = np.exp(rng.uniform(0, np.log(3000), size=40)).astype(int)
+    strings = [support.random_strings(rng, 1, int(n), int(n), support.PROTEIN)[0] for n in lengths]
+    queries, candidates = strings[:17], strings[17:] + [b""]
+    byte_to_class, costs = scoring.blosum62()
+    for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+        got = engine_type(byte_to_class, costs, open=-4, extend=-1)(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_weighted(queries, candidates, byte_to_class, costs, -4, -1, local))
+    got = szb.LevenshteinDistances()(queries, candidates, device=scope)
+    assert np.array_equal(got, support.oracle_levenshtein(queries, candidates))
+
+
+def test_shapes_and_degenerate_inputs(scope):
+    """1xN, Nx1, 1x1, ragged with empties, Nx0 / 0xN / 0x0 (reference test/similarities.cuh:1187-1326)."""
+    rng = np.random.default_rng(3)
+    engine = szb.LevenshteinDistances()
+    pool = support.random_strings(rng, 9, 0, 40, b"ab") + [b"", b""]
+    for queries, candidates in ((pool[:1], pool), (pool, pool[:1]), (pool[:1], pool[1:2]), (pool, pool[::-1]),
+                                ([b""], [b""]), ([b""], [b"xyz"]), ([b"xyz"], [b""])):
+        got = engine(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(queries, candidates))
+    assert engine([], pool, device=scope).shape == (0, len(pool))
+    assert engine(pool, [], device=scope).shape == (len(pool), 0)
+    assert engine([], [], device=scope).shape == (0, 0)
+    sample = b"ADVERSARIAL"
+    for gap in (1, 3):
+        tuned = szb.LevenshteinDistances(0, 1, gap, gap)
+        assert int(tuned([sample], [b""], device=scope)[0, 0]) == len(sample) * gap
+        assert int(tuned([sample], [sample], device=scope)[0, 0]) == 0
+
+
+def test_symmetric_self_similarity(scope):
+    rng = np.random.default_rng(5)
+    strings = support.random_strings(rng, 21, 0, 300, support.DNA)
+    matrix = szb.LevenshteinDistances()(strings, device=scope)
+    assert np.array_equal(matrix, support.oracle_levenshtein(strings, None))
+    assert np.array_equal(matrix, matrix.T) and not matrix.diagonal().any()
+    byte_to_class, costs = scoring.blosum62()
+    proteins = support.random_strings(rng, 15, 1, 200, support.PROTEIN)
+    for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+        got = engine_type(byte_to_class, costs, open=-4, extend=-1)(proteins, device=scope)
+        assert np.array_equal(got, support.oracle_weighted(proteins, None, byte_to_class, costs, -4, -1, local))
+
+
+def test_asymmetric_substitution_table(scope):
+    """cost[class(query)][class(candidate)] — the query indexes the row (SURVEY §7 'hard parts')."""
+    rng = np.random.default_rng(8)
+    byte_to_class, costs = scoring.uniform(b"ACGT", 2, -1)
+    costs = costs.copy()
+    costs[1, 2], costs[2, 1], costs[3, 4], costs[4, 3] = -3, 1, 0, -2
+    queries = support.random_strings(rng, 11, 1, 300, support.DNA)
+    candidates = support.mutated_copies(rng, queries, 0.2, support.DNA)
+    for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+        for gaps in ((-2, -2), (-3, -1)):
+            got = engine_type(byte_to_class, costs, open=gaps[0], extend=gaps[1])(queries, candidates, device=scope)
+            assert np.array_equal(got, support.oracle_weighted(queries, candidates, byte_to_class, costs, *gaps, local))
+        got = engine_type(byte_to_class, costs, open=-2, extend=-1)(queries, device=scope)
+        assert np.array_equal(got, support.oracle_weighted(queries, None, byte_to_class, costs, -2, -1, local))
+
+
+def test_large_alphabets_and_wide_cells(scope):
+    """More than 31 distinct bytes -> byte-compare recurrences; high costs -> 32-bit cells (test/similarities.cuh:2023)."""
+    rng = np.random.default_rng(13)
+    every_byte = bytes(range(256))
+    queries = support.random_strings(rng, 9, 0, 700, every_byte)
+    candidates = support.mutated_copies(rng, queries, 0.3, every_byte)
+    for costs in ((0, 1, 1, 1), (1, 3, 4, 2)):
+        got = szb.LevenshteinDistances(*costs)(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs))
+    binary_q = support.random_strings(rng, 5, 600, 800, b"ab")
+    binary_c = support.random_strings(rng, 6, 600, 800, b"ab")
+    for costs in ((0, 100, 100, 100), (0, 127, 90, 60)):
+        engine = szb.LevenshteinDistances(*costs)
+        got = engine(binary_q, binary_c, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(binary_q, binary_c, *costs))
+        assert engine.last_call_stats.pairs_s32 > 0
+    byte_to_class, table = scoring.uniform(b"ab", 100, -100)
+    got = szb.NeedlemanWunschScores(byte_to_class, table, open=-100, extend=-100)(binary_q, binary_c, device=scope)
+    assert np.array_equal(got, support.oracle_weighted(binary_q, binary_c, byte_to_class, table, -100, -100, False))
+
+
+def test_unusual_cost_signs_take_the_literal_tier(scope):
+    """Gap rewards and opening cheaper than extending defeat the packed recurrences' preconditions."""
+    rng = np.random.default_rng(17)
+    byte_to_class, table = scoring.blosum62()
+    queries = support.random_strings(rng, 7, 0, 150, support.PROTEIN)
+    candidates = support.random_strings(rng, 6, 0, 150, support.PROTEIN)
+    for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+        for gaps in ((-1, -4), (-2, 1), (1, 1), (3, -2)):
+            got = engine_type(byte_to_class, table, open=gaps[0], extend=gaps[1])(queries, candidates, device=scope)
+            want = support.oracle_weighted(queries, candidates, byte_to_class, table, *gaps, local)
+            assert np.array_equal(got, want), (engine_type.__name__, gaps)
+
+
+def test_every_input_layout_of_the_abi(scope):
+    """u32 tapes, u64 tapes and callback sequences; a row stride wider than the matrix; `out=` reuse."""
+    rng = np.random.default_rng(19)
+    queries = support.random_strings(rng, 6, 0, 90, support.DNA)
+    candidates = support.random_strings(rng, 5, 0, 90, support.DNA)
+    want = support.oracle_levenshtein(queries, candidates)
+    lib = _abi.bind()
+    engine = szb.LevenshteinDistances()
+    q, c = szb.Tape(queries), szb.Tape(candidates)
+
+    wide = np.full((len(queries), 9), 0xDEAD, dtype=np.uint64)
+    out = engine(q, c, device=scope, out=wide[:, :5])
+    assert np.array_equal(out, want) and (wide[:, 5:] == 0xDEAD).all()
+
+    q32, c32 = q.offsets.astype(np.uint32), c.offsets.astype(np.uint32)
+    tq = _abi.SequenceU32Tape(q.data.ctypes.data, q32.ctypes.data, len(q))
+    tc = _abi.SequenceU32Tape(c.data.ctypes.data, c32.ctypes.data, len(c))
+    got = np.zeros_like(want)
+    message = ct.c_char_p()
+    status = lib.szs_levenshtein_distances_u32tape(engine._handle, scope.handle, ct.byref(tq), ct.byref(tc),
+                                                   got.ctypes.data, 5, ct.byref(message))
+    assert status == 0 and np.array_equal(got, want)
+
+    def sequence_of(strings):
+        buffers = [ct.create_string_buffer(s, len(s)) if s else ct.create_string_buffer(1) for s in strings]
+        start = _abi.SEQUENCE_START(lambda _, i: ct.addressof(buffers[i]))
+        length = _abi.SEQUENCE_LENGTH(lambda _, i: len(strings[i]))
+        return _abi.Sequence(None, len(strings), start, length), (buffers, start, length)
+
+    sq, keep_q = sequence_of(queries)
+    sc, keep_c = sequence_of(candidates)
+    got = np.zeros_like(want)
+    status = lib.szs_levenshtein_distances(engine._handle, scope.handle, ct.byref(sq), ct.byref(sc), got.ctypes.data,
+                                           5, ct.byref(message))
+    assert status == 0 and np.array_equal(got, want)
+
+
+def test_row_shards_reassemble_the_matrix(scope):
+    rng = np.random.default_rng(23)
+    queries = support.random_strings(rng, 13, 0, 200, support.DNA)
+    candidates = support.random_strings(rng, 7, 0, 200, support.DNA)
+    engine = szb.LevenshteinDistances(1, 3, 3, 3)
+    out = np.zeros((13, 7), dtype=np.uint64)
+    for begin, end in ((0, 4), (4, 5), (5, 13)):
+        engine.score_rows(queries, candidates, begin, end, device=scope, out=out)
+    assert np.array_equal(out, support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3))
+
+
+def test_full_size_tile_properties_and_sampled_parity(scope):
+    """BASELINE config 2 scale (q316 x c317, |s| ~ 1024): size-independent properties over the whole matrix plus
+    exact parity on sampled rows (the oracle would need minutes for all 1e11 cells)."""
+    rng = np.random.default_rng(42)
+    queries = support.random_strings(rng, 316, 960, 1088, support.DNA)
+    candidates = support.mutated_copies(rng, queries[:200], 0.1, support.DNA) + support.random_strings(
+        rng, 117, 960, 1088, support.DNA)
+    engine = szb.LevenshteinDistances()
+    matrix = engine(queries, candidates, device=scope)
+    lengths_q = np.array([len(s) for s in queries])[:, None]
+    lengths_c = np.array([len(s) for s in candidates])[None, :]
+    assert (matrix >= np.abs(lengths_q - lengths_c)).all() and (matrix <= np.maximum(lengths_q, lengths_c)).all()
+    rows = [0, 57, 199, 315]
+    want = support.oracle_levenshtein([queries[r] for r in rows], candidates)
+    assert np.array_equal(matrix[rows], want)
+    # Swapping the sides transposes the matrix (unit costs are symmetric).
+    transposed = engine(candidates, queries, device=scope)
+    assert np.array_equal(transposed, matrix.T)
+    stats = engine.last_call_stats
+    assert stats.cells == int(lengths_q.sum()) * int(lengths_c.sum()) and stats.kernel_launches >= 1
