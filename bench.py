@@ -1,0 +1,432 @@
+#!/usr/bin/env python3
+"""bench.py — cell-updates/s of the batched string-similarity hot path, one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A *step* is one pass of the hot path over one synthetic tile: a single `szs_*_u64tape` cross-product call.
+The default workload is BASELINE.json `configs[1]`: ~100k (query, candidate) pairs of DNA strings with lengths
+uniform on [960, 1088], unit-cost Levenshtein — the tile `q316 x c317` of SURVEY.md §8(d).
+
+Numbers on the line
+  value        GCUPS with the strings already resident in HBM and the score matrix left in HBM; time = CUDA events
+               recorded by the library on the stream its kernels run on (staging D2D + scheduling + kernels + D2D),
+               max over ranks.
+  e2e          the same metric through the C-ABI call with pinned HOST buffers: H2D of the strings and D2H of the
+               score matrix inside the timed region (wall clock around the synchronous calls, max over ranks).
+  roofline     the wavefront kernel against the int16-DPX issue roofline measured live by tools/microbench/pipe_rates.
+  cpu_baseline the reference's own CPU library (oracle/_ref) on this box's host cores, same tile.
+N > 1 (launched by torch.distributed.run): weak scaling — the tile grows to 316*N query rows, rank r scores its row
+block (balanced by total query length); the e2e leg broadcasts the inputs from rank 0 and gathers the score slabs there
+over NCCL.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as ct
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+DNA = b"ACGT"
+PROTEIN = b"ARNDCQEGHILKMFPSTWYV"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Workloads (fixed seed 42)
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def random_strings(rng, count, low, high, alphabet, log_uniform=False):
+    symbols = np.frombuffer(alphabet, dtype=np.uint8)
+    if log_uniform:
+        lengths = np.exp(rng.uniform(np.log(low), np.log(high), size=count)).astype(np.int64)
+    else:
+        lengths = rng.integers(low, high + 1, size=count)
+    return [symbols[rng.integers(0, len(symbols), size=int(n))].tobytes() for n in lengths]
+
+
+def make_workload(name: str, scale: int = 1):
+    """Returns (description, family, engine_kwargs, queries, candidates). `scale` multiplies the query rows (weak scaling)."""
+    from stringzilla_b200 import scoring
+
+    rng = np.random.default_rng(42)
+    if name in ("c2", "c2_weird", "c1"):
+        if name == "c1":
+            rows, cols, low, high = 32, 32, 64, 256
+        else:
+            rows, cols, low, high = 316, 317, 960, 1088
+        queries = random_strings(rng, rows * scale, low, high, DNA)
+        candidates = random_strings(rng, cols, low, high, DNA)
+        costs = dict(match=0, mismatch=1, open=1, extend=1) if name != "c2_weird" else dict(match=1, mismatch=3, open=3, extend=3)
+        label = f"{name}: q{rows * scale} x c{cols} DNA, len U[{low},{high}], Levenshtein costs {tuple(costs.values())}"
+        return label, "levenshtein", costs, queries, candidates
+    if name in ("c3", "c3_linear", "c3_sw", "c4", "c5"):
+        byte_to_class, table = scoring.blosum62()
+        if name == "c4":
+            rows, cols = 1000, 1000
+            queries = random_strings(rng, rows * scale, 32, 4096, PROTEIN, log_uniform=True)
+            candidates = random_strings(rng, cols, 32, 4096, PROTEIN, log_uniform=True)
+            family = "smith_waterman"
+        elif name == "c5":
+            rows, cols = 10000, 10000
+            queries = random_strings(rng, rows * scale, 480, 544, PROTEIN)
+            candidates = random_strings(rng, cols, 480, 544, PROTEIN)
+            family = "needleman_wunsch"
+        else:
+            rows, cols = 316, 317
+            queries = random_strings(rng, rows * scale, 960, 1088, PROTEIN)
+            candidates = random_strings(rng, cols, 960, 1088, PROTEIN)
+            family = "smith_waterman" if name == "c3_sw" else "needleman_wunsch"
+        gaps = dict(open=-4, extend=-4) if name == "c3_linear" else dict(open=-4, extend=-1)
+        label = f"{name}: q{rows * scale} x c{cols} protein, {family} BLOSUM62 gaps {tuple(gaps.values())}"
+        return label, family, dict(byte_to_class=byte_to_class, class_substitution_costs=table, **gaps), queries, candidates
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_engine(family, kwargs, library_path=None, capabilities=None):
+    import stringzilla_b200 as szb
+
+    extra = dict(library_path=library_path, capabilities=capabilities)
+    if family == "levenshtein":
+        return szb.LevenshteinDistances(**kwargs, **extra)
+    engine_type = szb.NeedlemanWunschScores if family == "needleman_wunsch" else szb.SmithWatermanScores
+    return engine_type(**kwargs, **extra)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Clocks sampled DURING the timed region
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, device_index: int):
+        self.device_index, self.samples, self.process = device_index, [], None
+
+    def __enter__(self):
+        try:
+            self.process = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.process = None
+        return self
+
+    def _read(self):
+        for line in self.process.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.samples.append(parts)
+
+    def __exit__(self, *exc):
+        if self.process:
+            time.sleep(0.15)
+            self.process.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        clocks = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        if not clocks:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [c for c in clocks if c > 0.5 * max(clocks)] or clocks
+        reasons = set()
+        for s in self.samples:
+            for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
+                "samples": len(clocks)}  # fmt: skip
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference arm / CPU baseline: the reference's own CPU library (oracle/_ref), all host threads
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def time_reference(family, kwargs, queries, candidates, steps, warmup, budget_seconds=60.0):
+    """Times the unmodified reference CPU build through its C ABI. Tries the serial and the SIMD capability masks with
+    all allowed cores and keeps the faster (the survey found the SIMD engines not always faster when threaded)."""
+    import stringzilla_b200 as szb
+    from stringzilla_b200 import _abi
+
+    ref = ROOT / "oracle" / "_ref" / "libstringzillas_ref.so"
+    if not ref.exists():
+        return None
+    q, c = szb.Tape(queries), szb.Tape(candidates)
+    cells = int(q.lengths.sum()) * int(c.lengths.sum())
+    scope = szb.DeviceScope(cpu_cores=0, library_path=ref)
+    cores = scope.cpu_cores
+    full = szb.capabilities(ref)
+    best = None
+    for label, caps in (("simd", full), ("serial", _abi.CAP_SERIAL | _abi.CAP_PARALLEL)):
+        engine = make_engine(family, kwargs, library_path=ref, capabilities=caps)
+        out = np.zeros((len(q), len(c)), dtype=engine._result_dtype)
+        start = time.perf_counter()
+        engine(q, c, device=scope, out=out)  # warm-up, also sizes the budget
+        first = time.perf_counter() - start
+        reps = max(1, min(steps, int(budget_seconds / 2 / max(first, 1e-3))))
+        for _ in range(max(0, min(warmup - 1, reps))):
+            engine(q, c, device=scope, out=out)
+        times = []
+        for _ in range(reps):
+            start = time.perf_counter()
+            engine(q, c, device=scope, out=out)
+            times.append(time.perf_counter() - start)
+        mean = sum(times) / len(times)
+        result = {"label": label, "seconds_per_step": mean, "gcups": cells / mean / 1e9, "steps": reps, "cores": cores,
+                  "checksum": int(out.astype(np.uint64).sum() & 0xFFFFFFFF)}  # fmt: skip
+        if best is None or result["gcups"] > best["gcups"]:
+            best = result
+    best["cells"] = cells
+    return best
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Our arm
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+def dpx_peak_lane_ops_per_second():
+    binary = ROOT / "tools" / "microbench" / "pipe_rates"
+    if not binary.exists():
+        return None
+    try:
+        line = subprocess.run([str(binary), "--dpx-peak"], capture_output=True, text=True, timeout=60).stdout.strip()
+        return float(json.loads(line)["dpx_lane_ops_per_s"])
+    except Exception:
+        return None
+
+
+def run_ours(args):
+    import torch
+
+    import stringzilla_b200 as szb
+    from stringzilla_b200 import _abi, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if args.gpus != world and rank == 0 and distributed:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if distributed:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    label, family, kwargs, queries, candidates = make_workload(args.workload, scale=world)
+    q, c = szb.Tape(queries), szb.Tape(candidates)
+    blocks = sharding.partition_rows(q.lengths, world)
+    row_begin, row_end = blocks[rank]
+    cells_total = int(q.lengths.sum()) * int(c.lengths.sum())
+    cells_local = int(q.lengths[row_begin:row_end].sum()) * int(c.lengths.sum())
+
+    engine = make_engine(family, kwargs)
+    scope = szb.DeviceScope(gpu_device=local_rank)
+    lib = _abi.bind()
+    result_dtype = torch.int64
+
+    # ---- leg 1: strings resident in HBM, scores left in HBM -------------------------------------------------------
+    q_dev = torch.from_numpy(q.data).to(device)
+    c_dev = torch.from_numpy(c.data).to(device)
+    out_dev = torch.zeros((len(q), len(c)), dtype=result_dtype, device=device)
+    tq = _abi.SequenceU64Tape(q_dev.data_ptr(), q.offsets.ctypes.data, len(q))  # offsets are host metadata
+    tc = _abi.SequenceU64Tape(c_dev.data_ptr(), c.offsets.ctypes.data, len(c))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # larger than the 126 MB L2
+    message = ct.c_char_p()
+
+    def resident_step():
+        status = lib.szs_b200_scores_u64tape_rows(engine._family_index, engine._handle, scope.handle, ct.byref(tq),
+                                                  ct.byref(tc), row_begin, row_end, out_dev.data_ptr(), len(c),
+                                                  ct.byref(message))
+        _abi.check(status, message)
+        return engine.last_call_stats
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        resident_step()
+    device_ms, kernel_ms, launches = [], [], 0
+    barrier()
+    with ClockSampler(local_rank) as sampler:
+        for _ in range(args.steps):
+            flush.fill_(1)  # evict the tile from L2 between timed iterations (outside the per-step event pair)
+            torch.cuda.synchronize()
+            stats = resident_step()
+            device_ms.append(stats.total_milliseconds)
+            kernel_ms.append(stats.kernel_milliseconds)
+            launches += int(stats.kernel_launches)
+        barrier()
+    clocks = sampler.summary()
+    resident_seconds = sum(device_ms) / 1e3
+    kernel_seconds = sum(kernel_ms) / 1e3
+    last_stats = engine.last_call_stats
+
+    # ---- leg 2: end to end through the C ABI with pinned host buffers ------------------------------------------------
+    q_pin = torch.from_numpy(q.data).pin_memory()
+    c_pin = torch.from_numpy(c.data).pin_memory()
+    out_pin = torch.zeros((len(q), len(c)), dtype=result_dtype).pin_memory()
+    hq = _abi.SequenceU64Tape(q_pin.data_ptr(), q.offsets.ctypes.data, len(q))
+    hc = _abi.SequenceU64Tape(c_pin.data_ptr(), c.offsets.ctypes.data, len(c))
+
+    def e2e_step():
+        if not distributed:
+            function = getattr(lib, f"szs_{engine._family}_u64tape")
+            _abi.check(function(engine._handle, scope.handle, ct.byref(hq), ct.byref(hc), out_pin.data_ptr(), len(c),
+                                ct.byref(message)), message)
+            stats = engine.last_call_stats
+            return int(stats.h2d_bytes), int(stats.d2h_bytes)
+        # Rank 0 owns the host inputs: H2D there, one NCCL broadcast, row-sharded scoring, one NCCL gather, D2H.
+        q_tape = q if rank == 0 else None
+        c_tape = c if rank == 0 else None
+        qd, qo = sharding.broadcast_tape(q_tape, src=0, device=device)
+        cd, co = sharding.broadcast_tape(c_tape, src=0, device=device)
+        qo_host, co_host = qo.cpu().numpy().astype(np.uint64), co.cpu().numpy().astype(np.uint64)
+        ltq = _abi.SequenceU64Tape(qd.data_ptr(), qo_host.ctypes.data, len(qo_host) - 1)
+        ltc = _abi.SequenceU64Tape(cd.data_ptr(), co_host.ctypes.data, len(co_host) - 1)
+        _abi.check(lib.szs_b200_scores_u64tape_rows(engine._family_index, engine._handle, scope.handle, ct.byref(ltq),
+                                                    ct.byref(ltc), row_begin, row_end, out_dev.data_ptr(), len(c),
+                                                    ct.byref(message)), message)
+        full = sharding.gather_rows(out_dev[row_begin:row_end], blocks, len(c), dst=0)
+        if rank == 0:
+            out_pin.copy_(full, non_blocking=False)
+            return int(q.data.size + c.data.size + q.offsets.nbytes + c.offsets.nbytes), int(out_pin.numel() * 8)
+        return 0, 0
+
+    for _ in range(max(1, args.warmup)):
+        h2d, d2h = e2e_step()
+    barrier()
+    start = time.perf_counter()
+    for _ in range(args.steps):
+        h2d, d2h = e2e_step()
+    barrier()
+    e2e_seconds = time.perf_counter() - start
+
+    # ---- max over ranks -------------------------------------------------------------------------------------------
+    times = torch.tensor([resident_seconds, kernel_seconds, e2e_seconds], dtype=torch.float64, device=device)
+    if distributed:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    resident_seconds, kernel_seconds, e2e_seconds = (float(t) for t in times)
+
+    if rank == 0:
+        value = cells_total * args.steps / resident_seconds / 1e9
+        e2e_value = cells_total * args.steps / e2e_seconds / 1e9
+        kernel_gcups = cells_total * args.steps / kernel_seconds / 1e9
+        # Roofline: int16 DPX issue rate. Algorithmic DPX work per packed pair of cells: the reference formulation needs
+        # 2 (linear gaps) or 3 (affine) DPX-class instructions; this kernel's shifted linear
+        # recurrence needs 1 (VIMNMX3.U16x2). `peak` follows BASELINE.md's k; `dpx_pipe_frac` is this kernel's own
+        # DPX instructions over the measured DPX issue rate.
+        lane_ops = dpx_peak_lane_ops_per_second() if world == 1 else None
+        affine = kwargs.get("open") != kwargs.get("extend")
+        k_reference = 3 if affine else 2
+        k_ours = {"levenshtein": 3 if affine else 1, "needleman_wunsch": 3 if affine else 1,
+                  "smith_waterman": 4.5 if affine else 2.5}[family]  # fmt: skip
+        roofline = None
+        if lane_ops:
+            peak = lane_ops * 2 / k_reference / 1e9 * world
+            peaks_file = ROOT / "MEASURED_PEAKS.json"
+            hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
+            algorithmic_bytes = (int(q.data.size) + int(c.data.size)) + 8 * len(q) * len(c)
+            roofline = {
+                "bound": "dpx-int16-issue", "achieved": round(kernel_gcups, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                "frac": round(kernel_gcups / peak, 4), "traffic": None,
+                "dpx_lane_ops_per_s_measured": lane_ops, "dpx_instr_per_cell_pair": {"reference_formulation": k_reference, "this_kernel": k_ours},
+                "dpx_pipe_frac": round(kernel_gcups * 1e9 / 2 * k_ours / lane_ops, 4),
+                "hbm": {"achieved_gbs": round(algorithmic_bytes * args.steps / kernel_seconds / 1e9, 2),
+                        "peak_gbs": hbm_peak, "frac": round(algorithmic_bytes * args.steps / kernel_seconds / 1e9 / hbm_peak, 6),
+                        "peak_source": "MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"},
+                "kernel": "szb::wavefront_kernel", "kernel_ms_per_launch": round(kernel_seconds * 1e3 / args.steps, 4),
+            }  # fmt: skip
+        baseline = None
+        if world == 1 and not args.skip_cpu_baseline:
+            reference = time_reference(family, kwargs, queries, candidates, steps=3, warmup=1, budget_seconds=30)
+            if reference:
+                baseline = {"value": round(reference["gcups"], 2), "unit": "GCUPS", "cores": reference["cores"],
+                            "kind": "reference", "sample": f"the full tile ({reference['cells']:.3e} cell updates) x "
+                            f"{reference['steps']} steps, reference '{reference['label']}' capability mask, all allowed cores"}  # fmt: skip
+        line = {
+            "metric": "GCUPS (giga cell-updates/s), batched Levenshtein at |s|~1024" if args.workload == "c2" else f"GCUPS, {family}",
+            "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(resident_seconds * 1e3 / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u16x2 (packed int16 DPX cells)" if last_stats.pairs_u16 else "s32",
+            "data": "synthetic", "impl": "ours",
+            "config": {"workload": label, "tile_rows_per_gpu": len(q) // world, "l2": "flushed between timed iterations (256 MB fill)",
+                       "partition": f"query rows over {world} rank(s), balanced by total query length"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_seconds * 1e3 / args.steps, 4)},
+            "gpu_launches": launches, "kernel_only_gcups": round(kernel_gcups, 1),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": baseline,
+            "cells_per_step": cells_total,
+        }  # fmt: skip
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle/_ref), all host threads, same
+    config. Under torchrun only rank 0 runs; the other ranks exit 0 without work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    label, family, kwargs, queries, candidates = make_workload(args.workload, scale=1)
+    reference = time_reference(family, kwargs, queries, candidates, steps=args.steps, warmup=args.warmup, budget_seconds=120)
+    if reference is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libstringzillas_ref.so is not built"}))
+        return
+    value = round(reference["gcups"], 2)
+    sample = (f"one tile per step ({reference['cells']:.3e} cell updates), {reference['steps']} timed steps, reference "
+              f"'{reference['label']}' capability mask, szs_device_scope_init_cpu_cores(0)")
+    print(json.dumps({
+        "metric": "GCUPS (giga cell-updates/s), batched Levenshtein at |s|~1024" if args.workload == "c2" else f"GCUPS, {family}",
+        "value": value, "unit": "GCUPS", "n_gpus": world, "steps": reference["steps"], "warmup": args.warmup,
+        "ms_per_step": round(reference["seconds_per_step"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 bit-parallel / u8..u64 DP cells (reference CPU tiers)", "data": "synthetic",
+        "impl": "reference", "config": {"workload": label},
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": reference["cores"], "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))  # fmt: skip
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    parser.add_argument("--workload", default="c2")
+    parser.add_argument("--skip-cpu-baseline", action="store_true")
+    args = parser.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

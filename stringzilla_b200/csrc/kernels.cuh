@@ -393,7 +393,8 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
                                     else { score = __viaddmax_s32(max((int)h[k], (int)l), open, t); }
                                     if constexpr (local) {
                                         score = max(score, 0);
-                                        best = (uint32_t)max((int)best, score);
+                                        // Gap rewards can inflate padding columns: only real cells compete.
+                                        if (cbase + k < (int)slot.len0) best = (uint32_t)max((int)best, score);
                                     }
                                     l = h[k] = (uint32_t)score;
                                 }

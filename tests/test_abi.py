@@ -52,10 +52,17 @@ def test_device_scopes_host_side(library_built):
 
 
 def test_engine_lifecycle_without_gpu(library_built):
+    """Engines are plain host objects until the first call: init/free work on a CPU-only box."""
+    from stringzilla_b200 import scoring
+
     engine = szb.LevenshteinDistances(0, 1, 1, 1)
     assert engine._handle
-    byte_to_class, costs = szb.scoring.blosum62() if hasattr(szb, "scoring") else (None, None)
     del engine
+    byte_to_class, costs = scoring.blosum62()
+    for engine_type in (szb.NeedlemanWunschScores, szb.SmithWatermanScores):
+        assert engine_type(byte_to_class, costs, open=-4, extend=-1)._handle
+    with pytest.raises(ValueError):
+        szb.NeedlemanWunschScores(byte_to_class, costs[:8], open=-4, extend=-1)
 
 
 def test_no_cpu_fallback(library_built):

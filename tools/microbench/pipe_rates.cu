@@ -3,6 +3,7 @@
 // Output: one JSON line per op: warp-instructions per clock per SM (so x32 = lane-ops/clk/SM).
 #include <cstdio>
 #include <cstdint>
+#include <string>
 #include <cuda_runtime.h>
 
 #define ITERS 4096
@@ -114,7 +115,37 @@ void sweep(int sms, uint32_t *out, unsigned long long *cyc) {
     }
 }
 
-int main() {
+/** `--dpx-peak`: sustained VIMNMX3.U16x2 issue rate over ~50 launches, the denominator of the int16-DPX roofline. */
+static int dpx_peak() {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    int const sms = prop.multiProcessorCount, threads = 256, blocks = sms * 4;
+    uint32_t *out;
+    unsigned long long *cyc;
+    cudaMalloc(&out, sizeof(uint32_t) * blocks * threads);
+    cudaMalloc(&cyc, sizeof(unsigned long long) * blocks);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int i = 0; i < 5; ++i) bench<OP_VIMAX3_U16X2><<<blocks, threads, 16384>>>(out, 12345u, cyc);
+    cudaDeviceSynchronize();
+    int const launches = 60;
+    cudaEventRecord(e0);
+    for (int i = 0; i < launches; ++i) bench<OP_VIMAX3_U16X2><<<blocks, threads, 16384>>>(out, 12345u, cyc);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double const warp_instrs = (double)launches * ITERS * ILP * (threads / 32) * blocks;
+    double const lane_ops_per_s = warp_instrs * 32 / (ms * 1e-3);
+    printf("{\"op\": \"vimax3_u16x2\", \"sms\": %d, \"ms\": %.3f, \"dpx_lane_ops_per_s\": %.4e, "
+           "\"dpx_warp_instr_per_clk_per_sm_at_max_clock\": %.3f, \"max_clock_mhz\": %d, \"err\": \"%s\"}\n",
+           sms, ms, lane_ops_per_s, warp_instrs / (ms * 1e-3) / sms / (prop.clockRate * 1e3), prop.clockRate / 1000,
+           cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && std::string(argv[1]) == "--dpx-peak") return dpx_peak();
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
     int sms = prop.multiProcessorCount;
