@@ -184,15 +184,29 @@ static int visible_device_count() {
     return count;
 }
 
-/** Compute capability major*10+minor of a device, or 0. */
-static int device_sm_code(int device) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return prop.major * 10 + prop.minor;
+/** Cached (sm_code, multiprocessor count) per device: `cudaGetDeviceProperties` costs milliseconds per call. */
+struct DeviceFacts {
+    int sm_code = 0, sms = 0;
+};
+static DeviceFacts device_facts(int device) {
+    static std::mutex mutex;
+    static DeviceFacts cache[64];
+    static bool known[64] = {false};
+    std::lock_guard<std::mutex> lock(mutex);
+    if (device >= 0 && device < 64 && known[device]) return cache[device];
+    DeviceFacts facts;
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) == cudaSuccess &&
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) == cudaSuccess &&
+        cudaDeviceGetAttribute(&facts.sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess)
+        facts.sm_code = major * 10 + minor;
+    else cudaGetLastError();
+    if (device >= 0 && device < 64 && facts.sm_code) cache[device] = facts, known[device] = true;
+    return facts;
 }
+
+/** Compute capability major*10+minor of a device, or 0. */
+static int device_sm_code(int device) { return device_facts(device).sm_code; }
 
 #pragma endregion
 
@@ -488,7 +502,8 @@ static bool fits_s32(Engine const &engine, uint64_t total_length) {
 }
 
 struct LaunchPlan {
-    int family, shape;
+    int family, strip_index;
+    int widest_coverage; // sizes the dynamic shared memory of the launch
     uint32_t first_job, n_jobs;
 };
 
@@ -514,7 +529,8 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
                      size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
     if (scope.kind == Scope::kCpu)
         return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
-    if (visible_device_count() <= scope.gpu_device) return fail(sz_missing_gpu_k, "No CUDA device is visible");
+    if (device_sm_code(scope.gpu_device) == 0 && visible_device_count() <= scope.gpu_device)
+        return fail(sz_missing_gpu_k, "No CUDA device is visible");
     if (device_sm_code(scope.gpu_device) < 100)
         return fail(sz_missing_gpu_k, "stringzillas_b200 kernels require an sm_100-class (Blackwell) device");
     if (Failure failure = scope.ensure_stream()) return failure;
@@ -615,69 +631,79 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
 
     struct HostSlot {
         CandSlot slot;
-        int family, shape;
+        int family;
+        Shape shape;
     };
     std::vector<HostSlot> host_slots;
     host_slots.reserve(n_candidates);
     uint64_t cells_total = 0, cells_u16 = 0;
     uint64_t query_bytes_in_rows = 0;
     for (uint32_t q : order) query_bytes_in_rows += query_length(q);
+    // Affine recurrences keep two register strips per lane: cap their strip width at 32 columns to stay spill-free.
+    auto shape_of = [&](int family, uint32_t longest) {
+        Shape shape = shape_for_length(longest);
+        if (family_is_affine(family) && kStrips[shape.strip_index] > 32) {
+            uint32_t const passes = (longest + 1023) / 1024, width = (longest + passes - 1) / passes;
+            for (int i = 0; i < kStripCount; ++i)
+                if ((uint32_t)kStrips[i] * 32 >= width) return Shape {i, 32};
+        }
+        return shape;
+    };
     for (size_t i = 0; i < n_candidates;) {
         uint32_t const c0 = by_length[i], len0 = candidate_length(c0);
         bool const narrow0 = fits_u16(model, std::min<uint64_t>(len0, longest_query));
         if (narrow0 && i + 1 < n_candidates) {
             uint32_t const c1 = by_length[i + 1], len1 = candidate_length(c1);
             if (fits_u16(model, std::min<uint64_t>(len1, longest_query))) {
-                host_slots.push_back({{c0, c1, len0, len1}, model.family16, shape_for_length(len1)});
+                host_slots.push_back({{c0, c1, len0, len1}, model.family16, shape_of(model.family16, len1)});
                 cells_u16 += ((uint64_t)len0 + len1) * query_bytes_in_rows;
                 i += 2;
                 continue;
             }
         }
-        host_slots.push_back(
-            {{c0, kNoCandidate, len0, 0}, narrow0 ? model.family16 : model.family32, shape_for_length(len0)});
+        int const family = narrow0 ? model.family16 : model.family32;
+        host_slots.push_back({{c0, kNoCandidate, len0, 0}, family, shape_of(family, len0)});
         if (narrow0) cells_u16 += (uint64_t)len0 * query_bytes_in_rows;
         i += 1;
     }
     for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
 
-    // 6. Jobs: every slot crossed with blocks of the query order; grouped into one launch per (family, shape).
-    int device_sms = 148;
-    cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, scope.gpu_device);
+    // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
+    int const device_sms = std::max(1, device_facts(scope.gpu_device).sms);
     std::vector<Job> host_jobs;
     std::vector<LaunchPlan> plans;
     uint64_t scratch_words_per_cta = 0;
-    // Longest slots first: their jobs are the heaviest.
-    std::vector<uint32_t> slot_order(host_slots.size());
-    std::iota(slot_order.begin(), slot_order.end(), 0u);
     for (int family = 0; family < 8; ++family) {
-        for (int shape = kShapeCount - 1; shape >= 0; --shape) {
+        for (int strip = kStripCount - 1; strip >= 0; --strip) {
+            // Longest slots first: their jobs are the heaviest, and the atomic job counter hands them out in order.
             std::vector<uint32_t> members;
             for (uint32_t s = (uint32_t)host_slots.size(); s-- > 0;)
-                if (host_slots[s].family == family && host_slots[s].shape == shape) members.push_back(s);
+                if (host_slots[s].family == family && host_slots[s].shape.strip_index == strip) members.push_back(s);
             if (members.empty()) continue;
-            int const groups = 32 / kShapes[shape].g;
-            uint32_t const min_block = (uint32_t)(kThreads / 32) * groups; // one batch for every warp
-            uint64_t const target_jobs = (uint64_t)device_sms * 8;
-            uint64_t blocks = (target_jobs + members.size() - 1) / members.size();
-            blocks = std::max<uint64_t>(1, std::min<uint64_t>(blocks, (n_rows + min_block - 1) / min_block));
-            uint32_t const block_rows = (uint32_t)((n_rows + blocks - 1) / blocks);
-            LaunchPlan plan = {family, shape, (uint32_t)host_jobs.size(), 0};
+            LaunchPlan plan = {family, strip, 0, (uint32_t)host_jobs.size(), 0};
             bool const affine = family_is_affine(family);
-            for (uint32_t begin = 0; begin < n_rows; begin += block_rows) {
-                uint32_t const end = (uint32_t)std::min<uint64_t>(n_rows, (uint64_t)begin + block_rows);
-                for (uint32_t s : members) {
-                    CandSlot const &slot = host_slots[s].slot;
-                    uint32_t const longest = std::max(slot.len0, slot.len1);
-                    uint32_t scratch_words = 0;
-                    if (longest > (uint32_t)kShapes[shape].cols()) {
+            uint64_t const target_jobs = (uint64_t)device_sms * 8;
+            uint64_t const wanted_blocks = (target_jobs + members.size() - 1) / members.size();
+            for (uint32_t s : members) {
+                CandSlot const &slot = host_slots[s].slot;
+                Shape const shape = host_slots[s].shape;
+                plan.widest_coverage = std::max(plan.widest_coverage, shape.coverage());
+                // A block is a whole number of rounds of the CTA's warps (each sweeps 32 / G queries at a time),
+                // so that no warp idles at the job's barrier while others run an extra round.
+                uint32_t const round = (uint32_t)(kThreads / 32) * (32 / shape.lanes);
+                uint64_t const rounds_total = (n_rows + round - 1) / round;
+                uint64_t const blocks = std::max<uint64_t>(1, std::min<uint64_t>(wanted_blocks, rounds_total));
+                uint32_t const block_rows = (uint32_t)((rounds_total + blocks - 1) / blocks) * round;
+                uint32_t const longest = std::max(slot.len0, slot.len1);
+                for (uint32_t begin = 0; begin < n_rows; begin += block_rows) {
+                    uint32_t const end = (uint32_t)std::min<uint64_t>(n_rows, (uint64_t)begin + block_rows);
+                    if (longest > (uint32_t)shape.coverage()) {
                         uint64_t const rows = (uint64_t)query_length(order[begin]) + 1;
                         uint64_t const words = (uint64_t)(end - begin) * rows * (affine ? 2 : 1);
                         if (words > 0xFFFFFFFFull) return fail(sz_overflow_risk_k, "Boundary scratch too large");
-                        scratch_words = (uint32_t)words;
                         scratch_words_per_cta = std::max<uint64_t>(scratch_words_per_cta, words);
                     }
-                    host_jobs.push_back({s, begin, end, scratch_words});
+                    host_jobs.push_back({s, begin, end, (uint32_t)shape.lanes});
                 }
             }
             plan.n_jobs = (uint32_t)host_jobs.size() - plan.first_job;
@@ -712,7 +738,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
     if (scratch_words_per_cta) SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms));
 
-    // 8. Launch: one persistent grid per (family, shape), all on the scope's stream.
+    // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
     SZB_CUDA(cudaEventRecord(engine.events[1], stream));
     for (size_t p = 0; p < plans.size(); ++p) {
         LaunchPlan const &plan = plans[p];
@@ -731,8 +757,8 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         args.scratch = engine.scratch.as<uint32_t>();
         args.scratch_words_per_cta = scratch_words_per_cta;
         int const grid = (int)std::min<uint32_t>(plan.n_jobs, (uint32_t)device_sms);
-        size_t const smem = shared_bytes(plan.shape, model.scoring.n_classes, model.scoring.compare != 0);
-        SZB_CUDA(launch_wavefront(plan.family, plan.shape, grid, smem, stream, args));
+        size_t const smem = shared_bytes(plan.widest_coverage, model.scoring.n_classes, model.scoring.compare != 0);
+        SZB_CUDA(launch_wavefront(plan.family, plan.strip_index, grid, smem, stream, args));
         stats.kernel_launches++;
     }
     if (symmetric && whole_matrix && n_queries > 1) {

@@ -10,10 +10,9 @@
 
 namespace szb {
 
-template <int FAM, int SHAPE>
-static cudaError_t launch_shape(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
-    constexpr int K = kShapes[SHAPE].k, G = kShapes[SHAPE].g;
-    auto kernel = wavefront_kernel<FAM, K, G>;
+template <int FAM, int STRIP>
+static cudaError_t launch_strip(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
+    auto kernel = wavefront_kernel<FAM, kStrips[STRIP]>;
     // Opt in to the large dynamic shared-memory carve-out once per kernel and device.
     static bool configured[64] = {false};
     int device = 0;
@@ -28,13 +27,17 @@ static cudaError_t launch_shape(int grid, size_t smem, cudaStream_t stream, Kern
 }
 
 template <>
-cudaError_t launch_family<SZB_FAMILY>(int shape, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
-    switch (shape) {
-    case 0: return launch_shape<SZB_FAMILY, 0>(grid, smem, stream, args);
-    case 1: return launch_shape<SZB_FAMILY, 1>(grid, smem, stream, args);
-    case 2: return launch_shape<SZB_FAMILY, 2>(grid, smem, stream, args);
-    case 3: return launch_shape<SZB_FAMILY, 3>(grid, smem, stream, args);
-    default: return launch_shape<SZB_FAMILY, 4>(grid, smem, stream, args);
+cudaError_t launch_family<SZB_FAMILY>(int strip, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
+    switch (strip) {
+    case 0: return launch_strip<SZB_FAMILY, 0>(grid, smem, stream, args);
+    case 1: return launch_strip<SZB_FAMILY, 1>(grid, smem, stream, args);
+    case 2: return launch_strip<SZB_FAMILY, 2>(grid, smem, stream, args);
+    case 3: return launch_strip<SZB_FAMILY, 3>(grid, smem, stream, args);
+    case 4: return launch_strip<SZB_FAMILY, 4>(grid, smem, stream, args);
+    case 5: return launch_strip<SZB_FAMILY, 5>(grid, smem, stream, args);
+    case 6: return launch_strip<SZB_FAMILY, 6>(grid, smem, stream, args);
+    case 7: return launch_strip<SZB_FAMILY, 7>(grid, smem, stream, args);
+    default: return launch_strip<SZB_FAMILY, 8>(grid, smem, stream, args);
     }
 }
 

@@ -17,6 +17,9 @@
  *    2. lets each warp (or sub-warp group of G lanes) sweep one query over the profile: lane `l` owns K consecutive
  *       DP columns in registers and processes DP row `s - l` at step `s` (a skewed wavefront); the only inter-lane
  *       traffic is one `__shfl_up` of the strip's last cell per step (two for affine gaps).
+ *  K is a template parameter (the strip lives in registers), G is a run-time property of the job: the host picks
+ *  the (K, G) whose coverage K * G fits the slot's length most tightly, because the cost of a sweep is proportional
+ *  to K * G, not to the candidate's length.
  *  Profile rows are vector-interleaved ([vector v][lane l] -> 16 bytes) so that the LDS.128 of the 8 lanes of a
  *  quarter-warp covers all 32 banks whatever rows (classes) the lanes are reading: conflict-free by construction.
  *
@@ -76,9 +79,10 @@ struct CandSlot {
     uint32_t len0, len1; ///< lengths in bytes; len1 == 0 when unpaired
 };
 
-/** A slot scored against the queries `q_order[q_begin .. q_end)`. */
+/** A slot scored against the queries `q_order[q_begin .. q_end)` by wavefronts of `lanes` lanes per query. */
 struct Job {
-    uint32_t slot, q_begin, q_end, scratch_words; ///< scratch_words: multi-pass boundary storage this job needs
+    uint32_t slot, q_begin, q_end;
+    uint32_t lanes; ///< G: 8, 16 or 32 lanes sweep one query; a warp sweeps 32 / G queries at a time
 };
 
 struct KernelArgs {
@@ -130,55 +134,329 @@ __device__ __forceinline__ int64_t degenerate_score(int64_t len, int open, int e
     else return (int64_t)open * len;
 }
 
+/** Per-CTA constants of the recurrences, packed per half where a DPX instruction needs them bitwise. */
+struct SweepConstants {
+    int open, extend, bias, go, negate;
+    int cmp_match, cmp_mismatch;
+    bool compare;
+    uint32_t neg_go_bits;  // FAM_AFF_SHIFT: "- go" for VIADDMNMX
+    uint32_t bias_bits;    // FAM_SW_*: the zero floor in biased units
+    uint32_t gap_bits;     // FAM_SW_*: "+ open" for VIADDMNMX
+    uint32_t gap_arith;    // FAM_SW_LIN: "+ g" through a plain add
+    uint32_t ext_arith;    // FAM_SW_AFF: "+ extend" through a plain add
+};
+
 /**
- *  @brief One persistent CTA: pulls jobs, builds profiles, sweeps queries.
- *  @tparam FAM recurrence family, @tparam K DP columns per lane, @tparam G lanes per query (wavefront width).
+ *  @brief Sweeps one batch of 32 / G queries over the profile of one pass of a slot.
+ *  @tparam MULTI the slot needs several passes: strips exchange their edge column through `bnd` between passes.
  */
-template <int FAM, int K, int G>
-__global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const args) {
+template <int FAM, int K, bool MULTI>
+__device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstants const &sc, uint32_t const *prof,
+                                            CandSlot const &slot, Job const &job, uint8_t const *c0_ptr,
+                                            uint32_t batch, uint32_t n_queries, int pass, int passes, int G,
+                                            uint32_t *scratch) {
     using traits = family_traits<FAM>;
     constexpr bool packed = traits::packed, affine = traits::affine, local = traits::local;
-    constexpr int COLS = K * G;       // DP columns covered by one pass
-    constexpr int GROUPS = 32 / G;    // queries swept by one warp at a time
-    constexpr int VECS = K / 4;       // LDS.128 per lane per row
-    static_assert(K % 4 == 0 && G >= 8 && 32 % G == 0, "unsupported strip shape");
+    constexpr int VECS = K / 4;
+    constexpr uint32_t per_row = affine ? 2 : 1;
+    int const COLS = K * G, GROUPS = 32 / G;
+    int const lane = threadIdx.x & 31;
+    int const gl = lane & (G - 1), gi = lane / G;
+    int const open = sc.open, extend = sc.extend, bias = sc.bias, go = sc.go;
+    bool const compare = !packed && sc.compare;
+
+    uint32_t const q_pos = batch * GROUPS + gi;
+    bool const q_valid = q_pos < n_queries;
+    uint32_t const q = q_valid ? args.q_order[job.q_begin + q_pos] : 0;
+    uint32_t const q_begin_off = q_valid ? args.q_off[q] : 0;
+    int const m = q_valid ? (int)(args.q_off[q + 1] - q_begin_off) : 0;
+    uint8_t const *const q_ptr = args.q_cls + q_begin_off;
+
+    // Multi-pass boundary storage: the last DP column of the previous pass, one row-slot per query row.
+    // Queries of a job are sorted longest-first, so the job's first query bounds every row count.
+    uint32_t *bnd = nullptr;
+    if constexpr (MULTI) {
+        uint32_t const first = args.q_order[job.q_begin];
+        uint32_t const rows = args.q_off[first + 1] - args.q_off[first] + 1;
+        bnd = scratch + (size_t)q_pos * rows * per_row;
+    }
+
+    uint32_t const pass_base = (uint32_t)pass * COLS;
+    int const cbase = (int)pass_base + gl * K; // DP column left of this lane's strip
+    bool const first_strip = pass == 0 && gl == 0;
+    bool const from_scratch = MULTI && pass > 0 && gl == 0;
+    bool const to_scratch = MULTI && pass + 1 < passes && gl == G - 1;
+
+    // Top boundary: DP row 0 of the strip, and the seeds of the gap tracks.
+    uint32_t h[K], f[affine ? K : 1];
+    uint32_t cb[(!packed) ? VECS : 1]; // compare mode: the strip's raw candidate bytes
+    uint32_t diag_in, w_out = 0, e_out = 0, best = 0;
+    uint32_t left_boundary = 0, left_gap_boundary = 0; // pass 0, lane 0: DP column 0 (packed families: constant)
+    if constexpr (FAM == FAM_LIN_SHIFT) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = 0;
+        diag_in = 0;
+    }
+    else if constexpr (FAM == FAM_AFF_SHIFT) {
+        uint32_t const top = pack_bits(bias - go);
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = top, f[k] = 0;
+        diag_in = first_strip ? pack_bits(bias) : top;
+        left_boundary = top, left_gap_boundary = 0;
+    }
+    else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = sc.bias_bits;
+        if constexpr (affine) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) f[k] = pack_bits(bias + open + extend);
+        }
+        diag_in = sc.bias_bits;
+        best = sc.bias_bits;
+        left_boundary = sc.bias_bits, left_gap_boundary = pack_bits(bias + open + extend);
+    }
+    else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            int const top = (int)degenerate_score<FAM>(cbase + 1 + k, open, extend);
+            h[k] = (uint32_t)top;
+            if constexpr (affine) f[k] = (uint32_t)(top + open + extend);
+        }
+        diag_in = (uint32_t)(int)degenerate_score<FAM>(cbase, open, extend);
+        if (compare) {
+#pragma unroll
+            for (int v = 0; v < VECS; ++v) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t const col = (uint32_t)cbase + v * 4 + i;
+                    // Padding columns compare against byte 0; their cells are never read.
+                    uint32_t const byte = col < slot.len0 ? c0_ptr[col] : 0u;
+                    word |= (byte & 0xFFu) << (8 * i);
+                }
+                cb[v] = word;
+            }
+        }
+    }
+
+    // Number of steps: the longest query of the warp's groups plus the pipeline fill.
+    int steps = m > 0 ? m + G - 1 : 0;
+    for (int offset = 16; offset >= G; offset >>= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, offset));
+
+    uint32_t a_next = (gl == 0 && m > 0) ? q_ptr[0] : 0;
+    uint32_t bw_next = 0, be_next = 0;
+    if constexpr (MULTI) {
+        if (from_scratch && m > 0) {
+            bw_next = bnd[per_row];
+            if constexpr (affine) be_next = bnd[per_row + 1];
+        }
+    }
+    uint4 const *const strip_profile = (uint4 const *)prof + gl;
+
+    for (int s = 0; s < steps; ++s) {
+        int const r = s - gl + 1; // DP row processed in this step
+        bool const valid = r >= 1 && r <= m;
+
+        // Strip's left neighbour: the last cell of the lane to the left, one step ago.
+        uint32_t w_in = __shfl_up_sync(0xFFFFFFFFu, w_out, 1, G);
+        uint32_t e_in = 0;
+        if constexpr (affine) e_in = __shfl_up_sync(0xFFFFFFFFu, e_out, 1, G);
+        if (gl == 0) {
+            if (!MULTI || pass == 0) {
+                if constexpr (packed) { w_in = left_boundary, e_in = left_gap_boundary; }
+                else {
+                    w_in = (uint32_t)(int)degenerate_score<FAM>(r, open, extend);
+                    if constexpr (affine) e_in = w_in + (uint32_t)(open + extend);
+                }
+            }
+            else { w_in = bw_next, e_in = be_next; }
+        }
+
+        uint32_t const a = a_next;
+        {   // Prefetch the next row's class and (multi-pass) boundary cell.
+            int const next = s + 1 - gl;
+            bool const has_next = next >= 0 && next < m;
+            a_next = has_next ? q_ptr[next] : 0;
+            if constexpr (MULTI) {
+                if (from_scratch && has_next) {
+                    bw_next = bnd[(next + 1) * per_row];
+                    if constexpr (affine) be_next = bnd[(next + 1) * per_row + 1];
+                }
+            }
+        }
+
+        if (valid) {
+            uint32_t d = diag_in, l = w_in, e = e_in;
+            uint4 const *prow = strip_profile + (size_t)a * (COLS / 4);
+            int const a_int = (int)a;
+#pragma unroll
+            for (int v = 0; v < VECS; ++v) {
+                uint32_t p[4];
+                if (!compare) {
+                    uint4 const pv = *prow;
+                    prow += G;
+                    p[0] = pv.x, p[1] = pv.y, p[2] = pv.z, p[3] = pv.w;
+                }
+                else {
+                    if constexpr (!packed) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            p[i] = (uint32_t)(((cb[v] >> (8 * i)) & 0xFFu) == (uint32_t)a_int ? sc.cmp_match
+                                                                                              : sc.cmp_mismatch);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int const k = v * 4 + i;
+                    if constexpr (FAM == FAM_LIN_SHIFT) {
+                        uint32_t const t = d + p[i];
+                        d = h[k];
+                        l = h[k] = __vimax3_u16x2(t, h[k], l);
+                    }
+                    else if constexpr (FAM == FAM_AFF_SHIFT) {
+                        uint32_t const t = d + p[i];
+                        d = h[k];
+                        f[k] = __viaddmax_u16x2(h[k], sc.neg_go_bits, f[k]);
+                        e = __viaddmax_u16x2(l, sc.neg_go_bits, e);
+                        l = h[k] = __vimax3_u16x2(t, f[k], e);
+                    }
+                    else if constexpr (FAM == FAM_SW_LIN) {
+                        uint32_t const t = d + p[i];
+                        uint32_t const up_gap = h[k] + sc.gap_arith;
+                        d = h[k];
+                        uint32_t const x = __vimax3_u16x2(t, up_gap, sc.bias_bits);
+                        l = h[k] = __viaddmax_u16x2(l, sc.gap_bits, x);
+                        if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
+                    }
+                    else if constexpr (FAM == FAM_SW_AFF) {
+                        uint32_t const t = d + p[i];
+                        d = h[k];
+                        f[k] = __viaddmax_u16x2(h[k], sc.gap_bits, f[k] + sc.ext_arith);
+                        e = __viaddmax_u16x2(l, sc.gap_bits, e + sc.ext_arith);
+                        uint32_t const x = __vimax3_u16x2(t, f[k], sc.bias_bits);
+                        l = h[k] = __vmaxu2(x, e);
+                        if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
+                    }
+                    else { // signed 32-bit cells, literal recurrences
+                        int const t = (int)d + (int)p[i];
+                        d = h[k];
+                        int score;
+                        if constexpr (affine) {
+                            int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
+                            int const ins = __viaddmax_s32((int)l, open, (int)e + extend);
+                            f[k] = (uint32_t)del, e = (uint32_t)ins;
+                            score = __vimax3_s32(t, del, ins);
+                        }
+                        else { score = __viaddmax_s32(max((int)h[k], (int)l), open, t); }
+                        if constexpr (local) {
+                            score = max(score, 0);
+                            // Gap rewards can inflate padding columns: only real cells compete.
+                            if (cbase + k < (int)slot.len0) best = (uint32_t)max((int)best, score);
+                        }
+                        l = h[k] = (uint32_t)score;
+                    }
+                }
+            }
+            diag_in = w_in;
+            w_out = l, e_out = e;
+            if constexpr (MULTI) {
+                if (to_scratch) {
+                    bnd[r * per_row] = l;
+                    if constexpr (affine) bnd[r * per_row + 1] = e;
+                }
+            }
+        }
+    }
+
+    // Harvest: the cell (m, n) of each half for global alignments, the running maximum for local ones.
+#pragma unroll
+    for (int half = 0; half < (packed ? 2 : 1); ++half) {
+        uint32_t const cand = half == 0 ? slot.c0 : slot.c1;
+        if (cand == kNoCandidate) continue; // uniform across the CTA
+        int const n = (int)(half == 0 ? slot.len0 : slot.len1);
+        int64_t *const out = args.results + (uint64_t)(q - args.row_base) * args.stride + cand;
+
+        if constexpr (!local) {
+            if (m == 0 || n == 0) {
+                if (pass == 0 && gl == 0 && q_valid) {
+                    int64_t const score = degenerate_score<FAM>(m == 0 ? n : m, open, extend);
+                    *out = sc.negate ? -score : score;
+                }
+                continue;
+            }
+            if ((n - 1) / COLS != pass) continue; // uniform across the CTA
+            int const lane_star = ((n - 1) % COLS) / K, k_star = (n - 1) % K;
+            uint32_t cell = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (k == k_star) cell = h[k];
+            if (gl == lane_star && q_valid) {
+                int64_t score;
+                if constexpr (FAM == FAM_LIN_SHIFT)
+                    score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) + (int64_t)(m + n) * open;
+                else if constexpr (FAM == FAM_AFF_SHIFT)
+                    score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) - bias + (int64_t)(m + n) * extend;
+                else score = (int64_t)(int)cell;
+                *out = sc.negate ? -score : score;
+            }
+        }
+        else {
+            // Reduce the running maximum over the group's lanes.
+            uint32_t group_best = best;
+            for (int offset = G / 2; offset >= 1; offset >>= 1) {
+                uint32_t const other = __shfl_xor_sync(0xFFFFFFFFu, group_best, offset);
+                if constexpr (packed) group_best = __vmaxu2(group_best, other);
+                else group_best = (uint32_t)max((int)group_best, (int)other);
+            }
+            int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias : (int64_t)(int)group_best;
+            if (gl == 0 && q_valid) {
+                // Later passes of a long candidate fold into the cell written by pass 0 (same CTA, ordered by
+                // the pass barrier).
+                if (m == 0 || n == 0) score = 0;
+                if (pass == 0) *out = score;
+                else if (score > *out) *out = score;
+            }
+        }
+    }
+}
+
+/**
+ *  @brief One persistent CTA: pulls jobs, builds profiles, sweeps queries.
+ *  @tparam FAM recurrence family, @tparam K DP columns per lane (the register strip).
+ */
+template <int FAM, int K>
+__global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const args) {
+    using traits = family_traits<FAM>;
+    constexpr bool packed = traits::packed;
+    static_assert(K % 4 == 0, "strips are read as 16-byte vectors");
 
     extern __shared__ __align__(16) uint32_t smem[];
     Scoring const *const sc_global = args.scoring;
     int const n_classes = sc_global->n_classes;
-    bool const compare = !packed && sc_global->compare != 0;
-    uint32_t *const prof = smem; // [n_classes][COLS], vector-interleaved; absent in compare mode
-    int8_t *const sub = (int8_t *)(smem + (compare ? 0 : (size_t)n_classes * COLS)); // 1024 B
-    uint32_t *const ctl = (uint32_t *)(sub + 1024);                                  // [0] job index, [1] next batch
+    uint32_t *const ctl = smem;                // [0] job index, [1] next batch
+    int8_t *const sub = (int8_t *)(smem + 4);  // 1024 B
+    uint32_t *const prof = smem + 4 + 256;     // [n_classes][K * G], vector-interleaved; unused in compare mode
 
-    int const open = sc_global->open, extend = sc_global->extend, bias = sc_global->bias;
-    int const negate = sc_global->negate;
-    int const cmp_match = sc_global->match, cmp_mismatch = sc_global->mismatch;
-    int const go = extend - open;
+    SweepConstants sc;
+    sc.open = sc_global->open, sc.extend = sc_global->extend, sc.bias = sc_global->bias;
+    sc.go = sc.extend - sc.open, sc.negate = sc_global->negate;
+    sc.cmp_match = sc_global->match, sc.cmp_mismatch = sc_global->mismatch;
+    sc.compare = !packed && sc_global->compare != 0;
+    sc.neg_go_bits = pack_bits(-sc.go), sc.bias_bits = pack_bits(sc.bias), sc.gap_bits = pack_bits(sc.open);
+    sc.gap_arith = pack_arith(sc.open, sc.open), sc.ext_arith = pack_arith(sc.extend, sc.extend);
 
     for (int i = threadIdx.x; i < 256; i += kThreads) ((uint32_t *)sub)[i] = ((uint32_t const *)sc_global->sub)[i];
-
     int const lane = threadIdx.x & 31;
-    int const gl = lane % G, gi = lane / G;
-
-    // Constants of the recurrences, packed per half where the DPX instruction needs them bitwise.
-    uint32_t const k_neg_go = pack_bits(-go);          // FAM_AFF_SHIFT: "- go" for VIADDMNMX
-    uint32_t const k_bias = pack_bits(bias);           // FAM_SW_*: the zero floor in biased units
-    uint32_t const k_gap_bits = pack_bits(open);       // FAM_SW_*: "+ open" for VIADDMNMX
-    uint32_t const k_gap_arith = pack_arith(open, open);       // FAM_SW_LIN: "+ g" through a plain add
-    uint32_t const k_ext_arith = pack_arith(extend, extend);   // FAM_SW_AFF: "+ extend" through a plain add
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            ctl[0] = atomicAdd(args.job_counter, 1u);
-            ctl[1] = 0;
-        }
+        if (threadIdx.x == 0) ctl[0] = atomicAdd(args.job_counter, 1u);
         __syncthreads();
         uint32_t const job_index = ctl[0];
         if (job_index >= args.n_jobs) break;
         Job const job = args.jobs[job_index];
         CandSlot const slot = args.slots[job.slot];
+        int const G = (int)job.lanes, COLS = K * G, GROUPS = 32 / G;
         uint32_t const longest = max(slot.len0, slot.len1);
         int const passes = longest == 0 ? 1 : (int)((longest + COLS - 1) / COLS);
         uint8_t const *const c0_ptr = args.c_cls + args.c_off[slot.c0];
@@ -193,15 +471,15 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
             if (threadIdx.x == 0) ctl[1] = 0;
 
             // 1. Build the substitution profile of this slot's columns [pass_base, pass_base + COLS).
-            if (!compare) {
+            if (!sc.compare) {
                 for (int idx = threadIdx.x; idx < n_classes * COLS; idx += kThreads) {
-                    int const a = idx / COLS, j = idx % COLS;
+                    int const a = idx / COLS, j = idx - a * COLS;
                     uint32_t const col = pass_base + j;
                     bool const v0 = col < slot.len0, v1 = col < slot.len1;
                     int const b0 = v0 ? c0_ptr[col] : 0, b1 = v1 ? c1_ptr[col] : 0;
-                    int const e0 = profile_term<FAM>(sub, a, b0, v0, open, extend, bias);
-                    int const e1 = profile_term<FAM>(sub, a, b1, v1, open, extend, bias);
-                    int const strip = j / K, k = j % K;
+                    int const e0 = profile_term<FAM>(sub, a, b0, v0, sc.open, sc.extend, sc.bias);
+                    int const e1 = profile_term<FAM>(sub, a, b1, v1, sc.open, sc.extend, sc.bias);
+                    int const strip = j / K, k = j - strip * K;
                     int const word = ((k / 4) * G + strip) * 4 + (k % 4);
                     prof[a * COLS + word] = packed ? pack_arith(e0, e1) : (uint32_t)e0;
                 }
@@ -214,253 +492,11 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
                 if (lane == 0) batch = atomicAdd(&ctl[1], 1u);
                 batch = __shfl_sync(0xFFFFFFFFu, batch, 0);
                 if (batch >= n_batches) break;
-
-                uint32_t const q_pos = batch * GROUPS + gi;
-                bool const q_valid = q_pos < n_queries;
-                uint32_t const q = q_valid ? args.q_order[job.q_begin + q_pos] : 0;
-                uint32_t const q_begin_off = q_valid ? args.q_off[q] : 0;
-                int const m = q_valid ? (int)(args.q_off[q + 1] - q_begin_off) : 0;
-                uint8_t const *const q_ptr = args.q_cls + q_begin_off;
-
-                // Multi-pass boundary storage: the last DP column of the previous pass, one row-slot per query row.
-                // Queries of a job are sorted longest-first, so the job's first query bounds every row count.
-                uint32_t *bnd = nullptr;
-                if (passes > 1) {
-                    uint32_t const first = args.q_order[job.q_begin];
-                    uint32_t const rows = args.q_off[first + 1] - args.q_off[first] + 1;
-                    bnd = scratch + (size_t)q_pos * rows * (affine ? 2 : 1);
-                }
-
-                int const cbase = (int)pass_base + gl * K; // DP column left of this lane's strip
-                bool const first_strip = pass == 0 && gl == 0;
-
-                // Top boundary: DP row 0 of the strip, and the seeds of the gap tracks.
-                uint32_t h[K], f[affine ? K : 1];
-                uint32_t cb[(!packed) ? VECS : 1]; // compare mode: the strip's raw candidate bytes
-                uint32_t diag_in, w_out = 0, e_out = 0, best = 0;
-                if constexpr (FAM == FAM_LIN_SHIFT) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) h[k] = 0;
-                    diag_in = 0;
-                }
-                else if constexpr (FAM == FAM_AFF_SHIFT) {
-                    uint32_t const top = pack_bits(bias - go);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) h[k] = top, f[k] = 0;
-                    diag_in = first_strip ? pack_bits(bias) : top;
-                }
-                else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) h[k] = k_bias;
-                    if constexpr (affine) {
-#pragma unroll
-                        for (int k = 0; k < K; ++k) f[k] = pack_bits(bias + open + extend);
-                    }
-                    diag_in = k_bias;
-                    best = k_bias;
-                }
-                else {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        int const top = (int)degenerate_score<FAM>(cbase + 1 + k, open, extend);
-                        h[k] = (uint32_t)top;
-                        if constexpr (affine) f[k] = (uint32_t)(top + open + extend);
-                    }
-                    diag_in = (uint32_t)(int)degenerate_score<FAM>(cbase, open, extend);
-                    if (compare) {
-#pragma unroll
-                        for (int v = 0; v < VECS; ++v) {
-                            uint32_t word = 0;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                uint32_t const col = (uint32_t)cbase + v * 4 + i;
-                                uint32_t const byte = col < slot.len0 ? c0_ptr[col] : 0x100u; // never equal
-                                word |= (byte & 0xFFu) << (8 * i);
-                                // Padding columns compare against a real byte value; their cells are never read.
-                            }
-                            cb[v] = word;
-                        }
-                    }
-                }
-
-                // Number of steps: the longest query of the warp's groups plus the pipeline fill.
-                int steps = m > 0 ? m + G - 1 : 0;
-#pragma unroll
-                for (int offset = 16; offset >= G; offset >>= 1)
-                    steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, offset));
-
-                uint32_t a_next = (gl == 0 && m > 0) ? q_ptr[0] : 0;
-                uint32_t bw_next = 0, be_next = 0;
-                if (pass > 0 && gl == 0 && m > 0) {
-                    bw_next = bnd[affine ? 2 : 1];
-                    if constexpr (affine) be_next = bnd[3];
-                }
-
-                for (int s = 0; s < steps; ++s) {
-                    int const r = s - gl + 1; // DP row processed in this step
-                    bool const valid = r >= 1 && r <= m;
-
-                    // Strip's left neighbour: the last cell of the lane to the left, one step ago.
-                    uint32_t w_in = __shfl_up_sync(0xFFFFFFFFu, w_out, 1, G);
-                    uint32_t e_in = 0;
-                    if constexpr (affine) e_in = __shfl_up_sync(0xFFFFFFFFu, e_out, 1, G);
-                    if (gl == 0) {
-                        if (pass == 0) {
-                            if constexpr (FAM == FAM_LIN_SHIFT) w_in = 0;
-                            else if constexpr (FAM == FAM_AFF_SHIFT) w_in = pack_bits(bias - go), e_in = 0;
-                            else if constexpr (FAM == FAM_SW_LIN) w_in = k_bias;
-                            else if constexpr (FAM == FAM_SW_AFF) w_in = k_bias, e_in = pack_bits(bias + open + extend);
-                            else {
-                                w_in = (uint32_t)(int)degenerate_score<FAM>(r, open, extend);
-                                if constexpr (affine) e_in = w_in + (uint32_t)(open + extend);
-                            }
-                        }
-                        else { w_in = bw_next, e_in = be_next; }
-                    }
-
-                    uint32_t const a = a_next;
-                    {   // Prefetch the next row's class and (multi-pass) boundary cell.
-                        int const next = s + 1 - gl;
-                        bool const has_next = next >= 0 && next < m;
-                        a_next = has_next ? q_ptr[next] : 0;
-                        if (pass > 0 && gl == 0 && has_next) {
-                            bw_next = bnd[(next + 1) * (affine ? 2 : 1)];
-                            if constexpr (affine) be_next = bnd[(next + 1) * 2 + 1];
-                        }
-                    }
-
-                    if (valid) {
-                        uint32_t d = diag_in, l = w_in, e = e_in;
-                        uint4 const *const prow = (uint4 const *)(prof + (size_t)a * COLS) + gl;
-                        int const a_int = (int)a;
-#pragma unroll
-                        for (int v = 0; v < VECS; ++v) {
-                            uint32_t p[4];
-                            if (!compare) {
-                                uint4 const pv = prow[v * G];
-                                p[0] = pv.x, p[1] = pv.y, p[2] = pv.z, p[3] = pv.w;
-                            }
-                            else {
-                                if constexpr (!packed) {
-#pragma unroll
-                                    for (int i = 0; i < 4; ++i)
-                                        p[i] = (uint32_t)(((cb[v] >> (8 * i)) & 0xFFu) == (uint32_t)a_int ? cmp_match
-                                                                                                          : cmp_mismatch);
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                int const k = v * 4 + i;
-                                if constexpr (FAM == FAM_LIN_SHIFT) {
-                                    uint32_t const t = d + p[i];
-                                    d = h[k];
-                                    l = h[k] = __vimax3_u16x2(t, h[k], l);
-                                }
-                                else if constexpr (FAM == FAM_AFF_SHIFT) {
-                                    uint32_t const t = d + p[i];
-                                    d = h[k];
-                                    f[k] = __viaddmax_u16x2(h[k], k_neg_go, f[k]);
-                                    e = __viaddmax_u16x2(l, k_neg_go, e);
-                                    l = h[k] = __vimax3_u16x2(t, f[k], e);
-                                }
-                                else if constexpr (FAM == FAM_SW_LIN) {
-                                    uint32_t const t = d + p[i];
-                                    uint32_t const up_gap = h[k] + k_gap_arith;
-                                    d = h[k];
-                                    uint32_t const x = __vimax3_u16x2(t, up_gap, k_bias);
-                                    l = h[k] = __viaddmax_u16x2(l, k_gap_bits, x);
-                                    if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
-                                }
-                                else if constexpr (FAM == FAM_SW_AFF) {
-                                    uint32_t const t = d + p[i];
-                                    d = h[k];
-                                    f[k] = __viaddmax_u16x2(h[k], k_gap_bits, f[k] + k_ext_arith);
-                                    e = __viaddmax_u16x2(l, k_gap_bits, e + k_ext_arith);
-                                    uint32_t const x = __vimax3_u16x2(t, f[k], k_bias);
-                                    l = h[k] = __vmaxu2(x, e);
-                                    if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
-                                }
-                                else { // signed 32-bit cells, literal recurrences
-                                    int const t = (int)d + (int)p[i];
-                                    d = h[k];
-                                    int score;
-                                    if constexpr (affine) {
-                                        int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
-                                        int const ins = __viaddmax_s32((int)l, open, (int)e + extend);
-                                        f[k] = (uint32_t)del, e = (uint32_t)ins;
-                                        score = __vimax3_s32(t, del, ins);
-                                    }
-                                    else { score = __viaddmax_s32(max((int)h[k], (int)l), open, t); }
-                                    if constexpr (local) {
-                                        score = max(score, 0);
-                                        // Gap rewards can inflate padding columns: only real cells compete.
-                                        if (cbase + k < (int)slot.len0) best = (uint32_t)max((int)best, score);
-                                    }
-                                    l = h[k] = (uint32_t)score;
-                                }
-                            }
-                        }
-                        diag_in = w_in;
-                        w_out = l, e_out = e;
-                        if (gl == G - 1 && pass + 1 < passes) {
-                            bnd[r * (affine ? 2 : 1)] = l;
-                            if constexpr (affine) bnd[r * 2 + 1] = e;
-                        }
-                    }
-                }
-
-                // 3. Harvest: the cell (m, n) of each half for global alignments, the running maximum for local ones.
-#pragma unroll
-                for (int half = 0; half < (packed ? 2 : 1); ++half) {
-                    uint32_t const cand = half == 0 ? slot.c0 : slot.c1;
-                    if (cand == kNoCandidate) continue; // uniform across the CTA
-                    int const n = (int)(half == 0 ? slot.len0 : slot.len1);
-                    int64_t *const out = args.results + (uint64_t)(q - args.row_base) * args.stride + cand;
-
-                    if constexpr (!local) {
-                        if (m == 0 || n == 0) {
-                            if (pass == 0 && gl == 0 && q_valid) {
-                                int64_t const score = degenerate_score<FAM>(m == 0 ? n : m, open, extend);
-                                *out = negate ? -score : score;
-                            }
-                            continue;
-                        }
-                        if ((n - 1) / COLS != pass) continue; // uniform across the CTA
-                        int const lane_star = ((n - 1) % COLS) / K, k_star = (n - 1) % K;
-                        uint32_t cell = 0;
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-                            if (k == k_star) cell = h[k];
-                        if (gl == lane_star && q_valid) {
-                            int64_t score;
-                            if constexpr (FAM == FAM_LIN_SHIFT)
-                                score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) + (int64_t)(m + n) * open;
-                            else if constexpr (FAM == FAM_AFF_SHIFT)
-                                score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) - bias + (int64_t)(m + n) * extend;
-                            else score = (int64_t)(int)cell;
-                            *out = negate ? -score : score;
-                        }
-                    }
-                    else {
-                        // Reduce the running maximum over the group's lanes.
-                        uint32_t group_best = best;
-#pragma unroll
-                        for (int offset = G / 2; offset >= 1; offset >>= 1) {
-                            uint32_t const other = __shfl_xor_sync(0xFFFFFFFFu, group_best, offset);
-                            if constexpr (packed) group_best = __vmaxu2(group_best, other);
-                            else group_best = (uint32_t)max((int)group_best, (int)other);
-                        }
-                        int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias
-                                               : (int64_t)(int)group_best;
-                        if (gl == 0 && q_valid) {
-                            // Later passes of a long candidate fold into the cell written by pass 0 (same CTA,
-                            // ordered by the pass barrier).
-                            if (m == 0 || n == 0) score = 0;
-                            if (pass == 0) *out = score;
-                            else if (score > *out) *out = score;
-                        }
-                    }
-                }
+                if (passes > 1)
+                    sweep_batch<FAM, K, true>(args, sc, prof, slot, job, c0_ptr, batch, n_queries, pass, passes, G,
+                                              scratch);
+                else
+                    sweep_batch<FAM, K, false>(args, sc, prof, slot, job, c0_ptr, batch, n_queries, 0, 1, G, scratch);
             }
         }
     }

@@ -1,40 +1,61 @@
 /**
  *  @file launch.cuh
  *  @brief Host-visible launch table of the wavefront kernels. Each recurrence family is compiled in its own
- *         translation unit (`family.cu` with -DSZB_FAMILY=n) so the 40 instantiations build in parallel.
+ *         translation unit (`family.cu` with -DSZB_FAMILY=n) so the instantiations build in parallel.
  */
 #pragma once
 #include "kernels.cuh"
 
 namespace szb {
 
-/** Strip shapes: (K columns per lane, G lanes per query). COLS = K * G DP columns per pass. */
-struct StripShape {
-    int k, g;
-    constexpr int cols() const { return k * g; }
-};
-constexpr int kShapeCount = 5;
-constexpr StripShape kShapes[kShapeCount] = {{8, 8}, {16, 8}, {32, 8}, {32, 16}, {32, 32}};
+/** Register-strip widths the kernels are instantiated for; a wavefront of G = 8, 16 or 32 lanes covers K * G columns. */
+constexpr int kStripCount = 9;
+constexpr int kStrips[kStripCount] = {8, 12, 16, 20, 24, 28, 32, 36, 40};
+constexpr int kMaxCoverage = 40 * 32;
 
-/** Picks the narrowest shape whose single pass covers `longest` columns; longer candidates take several passes. */
-inline int shape_for_length(uint32_t longest) {
-    for (int i = 0; i < kShapeCount; ++i)
-        if (longest <= (uint32_t)kShapes[i].cols()) return i;
-    return kShapeCount - 1;
+struct Shape {
+    int strip_index; ///< index into kStrips
+    int lanes;       ///< G
+    int coverage() const { return kStrips[strip_index] * lanes; }
+};
+
+/**
+ *  Picks the (K, G) whose coverage K * G fits `longest` columns most tightly: the cost of sweeping a query over a
+ *  slot is proportional to the coverage, not to the candidate's length. Ties go to the wider strip (less per-step
+ *  overhead). Candidates longer than the widest shape are split into equal passes.
+ */
+inline Shape shape_for_length(uint32_t longest) {
+    Shape best = {kStripCount - 1, 32};
+    if (longest > (uint32_t)kMaxCoverage) {
+        uint32_t const passes = (longest + kMaxCoverage - 1) / kMaxCoverage;
+        uint32_t const width = (longest + passes - 1) / passes;
+        for (int i = 0; i < kStripCount; ++i)
+            if ((uint32_t)kStrips[i] * 32 >= width) return {i, 32};
+        return best;
+    }
+    int best_coverage = kMaxCoverage + 1;
+    for (int lanes = 8; lanes <= 32; lanes *= 2)
+        for (int i = 0; i < kStripCount; ++i) {
+            int const coverage = kStrips[i] * lanes;
+            if ((uint32_t)coverage < longest) continue;
+            if (coverage < best_coverage || (coverage == best_coverage && kStrips[i] > kStrips[best.strip_index]))
+                best = {i, lanes}, best_coverage = coverage;
+        }
+    return best;
 }
 
-/** Dynamic shared memory of one CTA: the profile, the 32x32 table and two control words. */
-inline size_t shared_bytes(int shape, int n_classes, bool compare) {
-    size_t const profile = compare ? 0 : (size_t)n_classes * kShapes[shape].cols() * 4;
-    return profile + 1024 + 16;
+/** Dynamic shared memory of one CTA: two control words, the 32x32 table, and the profile of the widest job. */
+inline size_t shared_bytes(int coverage, int n_classes, bool compare) {
+    size_t const profile = compare ? 0 : (size_t)n_classes * coverage * 4;
+    return 16 + 1024 + profile;
 }
 
 inline bool family_is_affine(int family) { return family == 1 || family == 3 || family == 5 || family == 7; }
 
 template <int FAM>
-cudaError_t launch_family(int shape, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args);
+cudaError_t launch_family(int strip_index, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args);
 
-cudaError_t launch_wavefront(int family, int shape, int grid, size_t smem, cudaStream_t stream,
+cudaError_t launch_wavefront(int family, int strip_index, int grid, size_t smem, cudaStream_t stream,
                              KernelArgs const &args);
 
 } // namespace szb
