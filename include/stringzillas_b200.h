@@ -294,8 +294,14 @@ typedef struct szs_b200_call_stats_t {
     sz_u64_t d2h_bytes;         /* bytes copied device -> host */
     sz_u64_t pairs_u16;         /* (query, candidate) cells scored by the packed int16 DPX tier */
     sz_u64_t pairs_s32;         /* cells scored by the 32-bit DPX tier */
+    sz_u64_t pairs_bit_parallel; /* cells scored by the bit-parallel unit-cost Levenshtein kernel */
 } szs_b200_call_stats_t;
 SZS_B200_API sz_status_t szs_b200_last_call_stats(void const *engine, szs_b200_call_stats_t *stats);
+
+/** Unit-cost byte-level Levenshtein normally runs the bit-parallel (Myers/Hyyro) kernel, as every reference backend
+ *  does (serial.hpp:2636-2642); `enabled = 0` keeps such engines on the int16 DPX wavefront tier (used by bench.py to
+ *  measure that tier on the headline workload). Results are identical either way. */
+SZS_B200_API sz_status_t szs_b200_set_bit_parallel(void *engine, int enabled);
 
 /** Score only query rows [row_begin, row_end) of the cross product; `results` still addresses the FULL matrix
  *  (`results[q * stride + c]`), rows outside the range are left untouched. This is the shard primitive of the

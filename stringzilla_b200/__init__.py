@@ -197,20 +197,24 @@ class _Engine:
 
 class LevenshteinDistances(_Engine):
     """Mirror of `stringzillas.LevenshteinDistances(match=0, mismatch=1, open=1, extend=1, capabilities=...)`
-    (python/stringzillas/similarities.c:63-91). Returns a `uint64` matrix."""
+    (python/stringzillas/similarities.c:63-91). Returns a `uint64` matrix.
+
+    `bit_parallel=False` (a B200 addition) keeps unit-cost engines on the int16 DPX wavefront tier."""
 
     _family = "levenshtein_distances"
     _family_index = 0
     _result_dtype = np.uint64
 
     def __init__(self, match: int = 0, mismatch: int = 1, open: int = 1, extend: int = 1, capabilities=None,
-                 library_path=None):  # fmt: skip
+                 library_path=None, bit_parallel: bool = True):  # fmt: skip
         super().__init__(library_path)
         message = ct.c_char_p()
         status = self._lib.szs_levenshtein_distances_init(
             match, mismatch, open, extend, None, _resolve_capabilities(capabilities, self._lib),
             ct.byref(self._handle), ct.byref(message))  # fmt: skip
         _abi.check(status, message)
+        if not bit_parallel:
+            self._lib.szs_b200_set_bit_parallel(self._handle, 0)
 
 
 class _Weighted(_Engine):

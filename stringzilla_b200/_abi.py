@@ -81,6 +81,7 @@ class CallStats(ct.Structure):
         ("d2h_bytes", ct.c_uint64),
         ("pairs_u16", ct.c_uint64),
         ("pairs_s32", ct.c_uint64),
+        ("pairs_bit_parallel", ct.c_uint64),
     ]
 
 
@@ -111,7 +112,7 @@ REFERENCE_SYMBOLS = [
     "szs_fingerprints_init", "szs_fingerprints_sequence", "szs_fingerprints_u32tape", "szs_fingerprints_u64tape",
     "szs_fingerprints_free",
 ]  # fmt: skip
-B200_SYMBOLS = ["szs_b200_last_call_stats", "szs_b200_scores_u64tape_rows"]
+B200_SYMBOLS = ["szs_b200_last_call_stats", "szs_b200_scores_u64tape_rows", "szs_b200_set_bit_parallel"]
 
 
 def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
@@ -161,6 +162,8 @@ def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
         lib.szs_b200_last_call_stats.restype = ct.c_int
         lib.szs_b200_scores_u64tape_rows.argtypes = [ct.c_int, vp, vp, vp, vp, u64, u64, vp, u64, err]
         lib.szs_b200_scores_u64tape_rows.restype = ct.c_int
+        lib.szs_b200_set_bit_parallel.argtypes = [vp, ct.c_int]
+        lib.szs_b200_set_bit_parallel.restype = ct.c_int
     return lib
 
 

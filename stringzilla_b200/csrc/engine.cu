@@ -15,6 +15,7 @@
  */
 #include "../../include/stringzillas_b200.h"
 #include "launch.cuh"
+#include "myers.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -258,10 +259,11 @@ struct Engine {
     int match = 0, mismatch = 1, open = 1, extend = 1;
     uint8_t byte_to_class[256] = {0};
     int8_t costs[32 * 32] = {0};
+    bool bit_parallel = true; // unit-cost Levenshtein may take the bit-parallel kernel (szs_b200_set_bit_parallel)
 
     // Grow-only device state, one set per engine: engines are not re-entrant.
     StagedSet queries, candidates;
-    DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch;
+    DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch, myers_candidates;
     PinnedBuffer upload, upload_model;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     int events_device = -1;
@@ -629,13 +631,47 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     std::stable_sort(by_length.begin(), by_length.end(),
                      [&](uint32_t a, uint32_t b) { return candidate_length(a) < candidate_length(b); });
 
+    // 5a. Unit-cost Levenshtein over a compact alphabet: candidates the bit-parallel kernel covers leave the DP tiers.
+    struct MyersLaunch {
+        int words;
+        std::vector<MyersCandidate> members; // longest first
+    };
+    std::vector<MyersLaunch> myers_launches;
+    uint64_t cells_myers = 0;
+    bool const unit_costs = engine.algorithm == Algorithm::kLevenshtein && engine.match == 0 && engine.mismatch == 1 &&
+                            engine.open == 1 && engine.extend == 1;
+    if (unit_costs && engine.bit_parallel && !model.scoring.compare) {
+        uint64_t query_bytes = 0;
+        for (uint32_t q : order) query_bytes += query_length(q);
+        std::vector<uint32_t> kept;
+        for (size_t i = n_candidates; i-- > 0;) { // longest first
+            uint32_t const c = by_length[i], length = candidate_length(c);
+            int words = 0, lanes = 0;
+            myers_shape_for_length(length, words, lanes);
+            // One warp's match table must fit a sixteenth of the shared memory, so sixteen warps stay resident.
+            bool const fits = words > 0 && (size_t)model.scoring.n_classes * 32 * words * 4 <= 12 * 1024;
+            if (!fits) {
+                kept.push_back(c);
+                continue;
+            }
+            auto launch = std::find_if(myers_launches.begin(), myers_launches.end(),
+                                       [&](MyersLaunch const &l) { return l.words == words; });
+            if (launch == myers_launches.end()) myers_launches.push_back({words, {}}), launch = myers_launches.end() - 1;
+            launch->members.push_back({c, (uint32_t)lanes});
+            cells_myers += (uint64_t)length * query_bytes;
+        }
+        std::reverse(kept.begin(), kept.end()); // back to ascending length for the slot builder
+        by_length.swap(kept);
+    }
+    size_t const n_dp_candidates = by_length.size();
+
     struct HostSlot {
         CandSlot slot;
         int family;
         Shape shape;
     };
     std::vector<HostSlot> host_slots;
-    host_slots.reserve(n_candidates);
+    host_slots.reserve(n_dp_candidates);
     uint64_t cells_total = 0, cells_u16 = 0;
     uint64_t query_bytes_in_rows = 0;
     for (uint32_t q : order) query_bytes_in_rows += query_length(q);
@@ -649,10 +685,10 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         }
         return shape;
     };
-    for (size_t i = 0; i < n_candidates;) {
+    for (size_t i = 0; i < n_dp_candidates;) {
         uint32_t const c0 = by_length[i], len0 = candidate_length(c0);
         bool const narrow0 = fits_u16(model, std::min<uint64_t>(len0, longest_query));
-        if (narrow0 && i + 1 < n_candidates) {
+        if (narrow0 && i + 1 < n_dp_candidates) {
             uint32_t const c1 = by_length[i + 1], len1 = candidate_length(c1);
             if (fits_u16(model, std::min<uint64_t>(len1, longest_query))) {
                 host_slots.push_back({{c0, c1, len0, len1}, model.family16, shape_of(model.family16, len1)});
@@ -667,6 +703,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         i += 1;
     }
     for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
+    (void)cells_myers;
 
     // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
     int const device_sms = std::max(1, device_facts(scope.gpu_device).sms);
@@ -719,7 +756,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     SZB_CUDA(engine.order.reserve(order_bytes));
     SZB_CUDA(engine.slots.reserve(slots_bytes));
     SZB_CUDA(engine.jobs.reserve(jobs_bytes));
-    SZB_CUDA(engine.counters.reserve(plans.size() * sizeof(uint32_t) + 64));
+    SZB_CUDA(engine.counters.reserve((plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64));
     SZB_CUDA(engine.upload.reserve(order_bytes + slots_bytes + jobs_bytes));
     {
         char *arena = (char *)engine.upload.ptr;
@@ -727,19 +764,70 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         std::memcpy(arena + cursor, order.data(), order_bytes);
         SZB_CUDA(cudaMemcpyAsync(engine.order.ptr, arena + cursor, order_bytes, cudaMemcpyHostToDevice, stream));
         cursor += order_bytes;
-        std::memcpy(arena + cursor, device_slots.data(), slots_bytes);
-        SZB_CUDA(cudaMemcpyAsync(engine.slots.ptr, arena + cursor, slots_bytes, cudaMemcpyHostToDevice, stream));
-        cursor += slots_bytes;
-        std::memcpy(arena + cursor, host_jobs.data(), jobs_bytes);
-        SZB_CUDA(cudaMemcpyAsync(engine.jobs.ptr, arena + cursor, jobs_bytes, cudaMemcpyHostToDevice, stream));
+        if (slots_bytes) {
+            std::memcpy(arena + cursor, device_slots.data(), slots_bytes);
+            SZB_CUDA(cudaMemcpyAsync(engine.slots.ptr, arena + cursor, slots_bytes, cudaMemcpyHostToDevice, stream));
+            cursor += slots_bytes;
+            std::memcpy(arena + cursor, host_jobs.data(), jobs_bytes);
+            SZB_CUDA(cudaMemcpyAsync(engine.jobs.ptr, arena + cursor, jobs_bytes, cudaMemcpyHostToDevice, stream));
+        }
         stats.h2d_bytes += order_bytes + slots_bytes + jobs_bytes;
     }
-    SZB_CUDA(cudaMemsetAsync(engine.counters.ptr, 0, plans.size() * sizeof(uint32_t) + 64, stream));
+    SZB_CUDA(cudaMemsetAsync(engine.counters.ptr, 0, (plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64, stream));
     SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
     if (scratch_words_per_cta) SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms));
 
+    // 7a. The bit-parallel launches' candidate lists.
+    std::vector<MyersCandidate> myers_flat;
+    for (MyersLaunch const &launch : myers_launches) myers_flat.insert(myers_flat.end(), launch.members.begin(), launch.members.end());
+    if (!myers_flat.empty()) {
+        SZB_CUDA(engine.myers_candidates.reserve(myers_flat.size() * sizeof(MyersCandidate)));
+        SZB_CUDA(cudaMemcpyAsync(engine.myers_candidates.ptr, myers_flat.data(), myers_flat.size() * sizeof(MyersCandidate),
+                                 cudaMemcpyHostToDevice, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream)); // `myers_flat` is pageable and local
+        stats.h2d_bytes += myers_flat.size() * sizeof(MyersCandidate);
+    }
+
     // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
     SZB_CUDA(cudaEventRecord(engine.events[1], stream));
+    {
+        size_t first = 0;
+        for (size_t l = 0; l < myers_launches.size(); ++l) {
+            MyersLaunch const &launch = myers_launches[l];
+            size_t const table_bytes = (size_t)model.scoring.n_classes * 32 * launch.words * 4;
+            int const warps = kThreads / 32;
+            size_t const smem = table_bytes * warps;
+            int const ctas_per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
+            int const resident_warps = device_sms * ctas_per_sm * warps;
+            // Enough tasks for ~16 per resident warp; a task is `batches_per_block` warp sweeps of one candidate.
+            uint32_t narrowest = 32;
+            for (MyersCandidate const &member : launch.members) narrowest = std::min(narrowest, 32u / member.lanes);
+            uint64_t const sweeps_per_candidate = (n_rows + narrowest - 1) / narrowest;
+            uint64_t const total_sweeps = sweeps_per_candidate * launch.members.size();
+            uint64_t const batches_per_block = std::max<uint64_t>(1, total_sweeps / ((uint64_t)resident_warps * 16));
+            uint64_t const blocks = (sweeps_per_candidate + batches_per_block - 1) / batches_per_block;
+            if (blocks * launch.members.size() > 0xFFFFFFF0ull) return fail(sz_overflow_risk_k, "Too many tasks");
+            MyersArgs args;
+            args.q_cls = q_classes, args.q_off = qs.device_offsets.as<uint32_t>();
+            args.c_cls = c_classes, args.c_off = cs.device_offsets.as<uint32_t>();
+            args.q_order = engine.order.as<uint32_t>();
+            args.candidates = engine.myers_candidates.as<MyersCandidate>() + first;
+            args.n_candidates = (uint32_t)launch.members.size();
+            args.n_rows = (uint32_t)n_rows;
+            args.blocks_per_candidate = (uint32_t)blocks;
+            args.batches_per_block = (uint32_t)batches_per_block;
+            args.task_counter = engine.counters.as<uint32_t>() + plans.size() + l;
+            args.n_classes = model.scoring.n_classes;
+            args.results = engine.results.as<int64_t>();
+            args.stride = n_candidates;
+            args.row_base = (uint32_t)row_begin;
+            uint64_t const tasks = blocks * launch.members.size();
+            int const grid = (int)std::min<uint64_t>((tasks + warps - 1) / warps, (uint64_t)device_sms * ctas_per_sm);
+            SZB_CUDA(launch_myers(launch.words, grid, kThreads, smem, stream, args));
+            stats.kernel_launches++;
+            first += launch.members.size();
+        }
+    }
     for (size_t p = 0; p < plans.size(); ++p) {
         LaunchPlan const &plan = plans[p];
         KernelArgs args;
@@ -789,7 +877,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         for (size_t i = 0; i < n_queries; ++i) squares += (uint64_t)query_length((uint32_t)i) * query_length((uint32_t)i);
         stats.cells = (cells_total + squares) / 2;
     }
-    stats.pairs_u16 = cells_u16, stats.pairs_s32 = cells_total - cells_u16;
+    stats.pairs_u16 = cells_u16, stats.pairs_s32 = cells_total - cells_u16 - cells_myers, stats.pairs_bit_parallel = cells_myers;
     engine.stats = stats;
     return ok();
 }
@@ -1083,6 +1171,12 @@ SZS_B200_API void szs_fingerprints_free(szs_fingerprints_t) {}
 SZS_B200_API sz_status_t szs_b200_last_call_stats(void const *engine, szs_b200_call_stats_t *stats) {
     if (!engine || !stats) return sz_status_unknown_k;
     *stats = static_cast<Engine const *>(engine)->stats;
+    return sz_success_k;
+}
+
+SZS_B200_API sz_status_t szs_b200_set_bit_parallel(void *engine, int enabled) {
+    if (!engine) return sz_status_unknown_k;
+    static_cast<Engine *>(engine)->bit_parallel = enabled != 0;
     return sz_success_k;
 }
 
