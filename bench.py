@@ -267,23 +267,40 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        resident_step()
-    device_ms, kernel_ms, launches = [], [], 0
-    barrier()
-    with ClockSampler(local_rank) as sampler:
-        for _ in range(args.steps):
-            flush.fill_(1)  # evict the tile from L2 between timed iterations (outside the per-step event pair)
-            torch.cuda.synchronize()
-            stats = resident_step()
-            device_ms.append(stats.total_milliseconds)
-            kernel_ms.append(stats.kernel_milliseconds)
-            launches += int(stats.kernel_launches)
+    def timed_resident(step_function, current_engine):
+        for _ in range(args.warmup):
+            step_function()
+        device_ms, kernel_ms, launches = [], [], 0
         barrier()
-    clocks = sampler.summary()
-    resident_seconds = sum(device_ms) / 1e3
-    kernel_seconds = sum(kernel_ms) / 1e3
-    last_stats = engine.last_call_stats
+        with ClockSampler(local_rank) as sampler:
+            for _ in range(args.steps):
+                flush.fill_(1)  # evict the tile from L2 between timed iterations (outside the per-step event pair)
+                torch.cuda.synchronize()
+                stats = step_function()
+                device_ms.append(stats.total_milliseconds)
+                kernel_ms.append(stats.kernel_milliseconds)
+                launches += int(stats.kernel_launches)
+            barrier()
+        return sum(device_ms) / 1e3, sum(kernel_ms) / 1e3, launches, sampler.summary(), current_engine.last_call_stats
+
+    resident_seconds, kernel_seconds, launches, clocks, last_stats = timed_resident(resident_step, engine)
+
+    # The int16 DPX wavefront tier on the same tile: unit-cost engines normally take the bit-parallel kernel, so the
+    # tier the north star names is measured by pinning the engine to it (identical results, see tests).
+    dpx_seconds = None
+    if family == "levenshtein" and last_stats.pairs_bit_parallel:
+        dpx_engine = make_engine(family, dict(kwargs, bit_parallel=False))
+
+        def dpx_step():
+            status = lib.szs_b200_scores_u64tape_rows(dpx_engine._family_index, dpx_engine._handle, scope.handle,
+                                                      ct.byref(tq), ct.byref(tc), row_begin, row_end,
+                                                      out_dev.data_ptr(), len(c), ct.byref(message))
+            _abi.check(status, message)
+            return dpx_engine.last_call_stats
+
+        reference_scores = out_dev.clone()
+        dpx_seconds = timed_resident(dpx_step, dpx_engine)
+        assert torch.equal(reference_scores[row_begin:row_end], out_dev[row_begin:row_end]), "tiers disagree"
 
     # ---- leg 2: end to end through the C ABI with pinned host buffers ------------------------------------------------
     q_pin = torch.from_numpy(q.data).pin_memory()
@@ -326,40 +343,62 @@ def run_ours(args):
     e2e_seconds = time.perf_counter() - start
 
     # ---- max over ranks -------------------------------------------------------------------------------------------
-    times = torch.tensor([resident_seconds, kernel_seconds, e2e_seconds], dtype=torch.float64, device=device)
+    dpx_pair = (dpx_seconds[0], dpx_seconds[1]) if dpx_seconds else (0.0, 0.0)
+    times = torch.tensor([resident_seconds, kernel_seconds, e2e_seconds, *dpx_pair], dtype=torch.float64, device=device)
     if distributed:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    resident_seconds, kernel_seconds, e2e_seconds = (float(t) for t in times)
+    resident_seconds, kernel_seconds, e2e_seconds, dpx_resident_seconds, dpx_kernel_seconds = (float(t) for t in times)
 
     if rank == 0:
         value = cells_total * args.steps / resident_seconds / 1e9
         e2e_value = cells_total * args.steps / e2e_seconds / 1e9
         kernel_gcups = cells_total * args.steps / kernel_seconds / 1e9
-        # Roofline: int16 DPX issue rate. Algorithmic DPX work per packed pair of cells: the reference formulation needs
-        # 2 (linear gaps) or 3 (affine) DPX-class instructions; this kernel's shifted linear
-        # recurrence needs 1 (VIMNMX3.U16x2). `peak` follows BASELINE.md's k; `dpx_pipe_frac` is this kernel's own
-        # DPX instructions over the measured DPX issue rate.
+        # Rooflines. Neither kernel is HBM-bound (~1e-5 algorithmic bytes per cell update): the bound is instruction
+        # issue on the integer (ALU) pipe, whose rate — identical for DPX *.16x2, LOP3, SHF and IADD3 on this part —
+        # is measured live by tools/microbench/pipe_rates --dpx-peak.
         lane_ops = dpx_peak_lane_ops_per_second() if world == 1 else None
         affine = kwargs.get("open") != kwargs.get("extend")
-        k_reference = 3 if affine else 2
-        k_ours = {"levenshtein": 3 if affine else 1, "needleman_wunsch": 3 if affine else 1,
-                  "smith_waterman": 4.5 if affine else 2.5}[family]  # fmt: skip
-        roofline = None
-        if lane_ops:
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
+        algorithmic_bytes = (int(q.data.size) + int(c.data.size)) + 8 * len(q) * len(c)
+
+        def hbm_block(seconds):
+            gbs = algorithmic_bytes * args.steps / seconds / 1e9
+            return {"achieved_gbs": round(gbs, 2), "peak_gbs": hbm_peak, "frac": round(gbs / hbm_peak, 6),
+                    "peak_source": "MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"}
+
+        def dpx_roofline(gcups, seconds):
+            # 2 (linear) or 3 (affine) DPX-class instructions per packed pair of int16 cells in the
+            # reference's formulation -> peak = lane_ops/s * 2 cells / k. `dpx_pipe_frac` counts THIS kernel's DPX
+            # instructions (1 per pair for the shifted linear recurrence) against the measured DPX issue rate.
+            k_reference = 3 if affine else 2
+            k_ours = {"levenshtein": 3 if affine else 1, "needleman_wunsch": 3 if affine else 1,
+                      "smith_waterman": 4.5 if affine else 2.5}[family]
             peak = lane_ops * 2 / k_reference / 1e9 * world
-            peaks_file = ROOT / "MEASURED_PEAKS.json"
-            hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0
-            algorithmic_bytes = (int(q.data.size) + int(c.data.size)) + 8 * len(q) * len(c)
-            roofline = {
-                "bound": "dpx-int16-issue", "achieved": round(kernel_gcups, 1), "peak": round(peak, 1), "unit": "GCUPS",
-                "frac": round(kernel_gcups / peak, 4), "traffic": None,
-                "dpx_lane_ops_per_s_measured": lane_ops, "dpx_instr_per_cell_pair": {"reference_formulation": k_reference, "this_kernel": k_ours},
-                "dpx_pipe_frac": round(kernel_gcups * 1e9 / 2 * k_ours / lane_ops, 4),
-                "hbm": {"achieved_gbs": round(algorithmic_bytes * args.steps / kernel_seconds / 1e9, 2),
-                        "peak_gbs": hbm_peak, "frac": round(algorithmic_bytes * args.steps / kernel_seconds / 1e9 / hbm_peak, 6),
-                        "peak_source": "MEASURED_PEAKS.json" if peaks_file.exists() else "fallback"},
-                "kernel": "szb::wavefront_kernel", "kernel_ms_per_launch": round(kernel_seconds * 1e3 / args.steps, 4),
-            }  # fmt: skip
+            return {"bound": "dpx-int16-issue", "achieved": round(gcups, 1), "peak": round(peak, 1), "unit": "GCUPS",
+                    "frac": round(gcups / peak, 4), "traffic": None, "kernel": "szb::wavefront_kernel",
+                    "dpx_instr_per_cell_pair": {"reference_formulation": k_reference, "this_kernel": k_ours},
+                    "dpx_pipe_frac": round(gcups * 1e9 / 2 * k_ours / lane_ops / world, 4),
+                    "lane_ops_per_s_measured": lane_ops, "hbm": hbm_block(seconds),
+                    "kernel_ms_per_launch": round(seconds * 1e3 / args.steps, 4)}
+
+        roofline, dpx_tier = None, None
+        if lane_ops and last_stats.pairs_bit_parallel:
+            # Bit-parallel kernel: 7 LOP3 + 2 SHF + 1 IADD3.X per 32-bit word = 10 ALU lane-ops per 32 DP cells.
+            peak = lane_ops * 32 / 10 / 1e9 * world
+            roofline = {"bound": "alu-issue (bit-parallel, 10 lane-ops per 32 cells)", "achieved": round(kernel_gcups, 1),
+                        "peak": round(peak, 1), "unit": "GCUPS", "frac": round(kernel_gcups / peak, 4), "traffic": None,
+                        "kernel": "szb::myers_kernel", "lane_ops_per_s_measured": lane_ops,
+                        "hbm": hbm_block(kernel_seconds),
+                        "kernel_ms_per_launch": round(kernel_seconds * 1e3 / args.steps, 4)}
+        elif lane_ops:
+            roofline = dpx_roofline(kernel_gcups, kernel_seconds)
+        if dpx_seconds:
+            dpx_kernel_gcups = cells_total * args.steps / dpx_kernel_seconds / 1e9
+            dpx_tier = {"note": "same tile, engine pinned to the int16 DPX wavefront tier (szs_b200_set_bit_parallel(0))",
+                        "value": round(cells_total * args.steps / dpx_resident_seconds / 1e9, 1), "unit": "GCUPS",
+                        "ms_per_step": round(dpx_resident_seconds * 1e3 / args.steps, 4),
+                        "roofline": dpx_roofline(dpx_kernel_gcups, dpx_kernel_seconds) if lane_ops else None}
         baseline = None
         if world == 1 and not args.skip_cpu_baseline:
             reference = time_reference(family, kwargs, queries, candidates, steps=3, warmup=1, budget_seconds=30)
@@ -371,14 +410,16 @@ def run_ours(args):
             "metric": "GCUPS (giga cell-updates/s), batched Levenshtein at |s|~1024" if args.workload == "c2" else f"GCUPS, {family}",
             "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(resident_seconds * 1e3 / args.steps, 4), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u16x2 (packed int16 DPX cells)" if last_stats.pairs_u16 else "s32",
+            "vs_baseline": None,
+            "dtype": ("u32 bit-vectors (bit-parallel)" if last_stats.pairs_bit_parallel else
+                      "u16x2 (packed int16 DPX cells)" if last_stats.pairs_u16 else "s32"),
             "data": "synthetic", "impl": "ours",
             "config": {"workload": label, "tile_rows_per_gpu": len(q) // world, "l2": "flushed between timed iterations (256 MB fill)",
                        "partition": f"query rows over {world} rank(s), balanced by total query length"},
             "e2e": {"value": round(e2e_value, 1), "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_seconds * 1e3 / args.steps, 4)},
             "gpu_launches": launches, "kernel_only_gcups": round(kernel_gcups, 1),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": baseline,
+            "clocks": clocks, "roofline": roofline, "dpx_tier": dpx_tier, "cpu_baseline": baseline,
             "cells_per_step": cells_total,
         }  # fmt: skip
         print(json.dumps(line))
@@ -415,7 +456,7 @@ def run_reference(args):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--steps", type=int, default=50)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
     parser.add_argument("--workload", default="c2")

@@ -266,6 +266,11 @@ struct Engine {
     DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch, myers_candidates;
     PinnedBuffer upload, upload_model;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
+    // Independent launches of one call (different strip widths, word counts, families) overlap their tails on side
+    // streams forked from, and joined back into, the scope's stream.
+    static constexpr int kSideStreams = 3;
+    cudaStream_t side_streams[kSideStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_event = nullptr, join_events[kSideStreams] = {nullptr, nullptr, nullptr};
     int events_device = -1;
     szs_b200_call_stats_t stats = {};
     std::mutex mutex;
@@ -273,6 +278,11 @@ struct Engine {
     ~Engine() {
         for (cudaEvent_t event : events)
             if (event) cudaEventDestroy(event);
+        for (cudaEvent_t event : join_events)
+            if (event) cudaEventDestroy(event);
+        if (fork_event) cudaEventDestroy(fork_event);
+        for (cudaStream_t stream : side_streams)
+            if (stream) cudaStreamDestroy(stream);
     }
 };
 
@@ -519,6 +529,14 @@ static Failure ensure_events(Engine &engine, int device) {
         if (event) cudaEventDestroy(event), event = nullptr;
         SZB_CUDA(cudaEventCreate(&event));
     }
+    for (int i = 0; i < Engine::kSideStreams; ++i) {
+        if (engine.side_streams[i]) cudaStreamDestroy(engine.side_streams[i]), engine.side_streams[i] = nullptr;
+        if (engine.join_events[i]) cudaEventDestroy(engine.join_events[i]), engine.join_events[i] = nullptr;
+        SZB_CUDA(cudaStreamCreateWithFlags(&engine.side_streams[i], cudaStreamNonBlocking));
+        SZB_CUDA(cudaEventCreateWithFlags(&engine.join_events[i], cudaEventDisableTiming));
+    }
+    if (engine.fork_event) cudaEventDestroy(engine.fork_event), engine.fork_event = nullptr;
+    SZB_CUDA(cudaEventCreateWithFlags(&engine.fork_event, cudaEventDisableTiming));
     engine.events_device = device;
     return ok();
 }
@@ -646,11 +664,12 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         std::vector<uint32_t> kept;
         for (size_t i = n_candidates; i-- > 0;) { // longest first
             uint32_t const c = by_length[i], length = candidate_length(c);
+            // One warp's match table (classes x 32 x W words) must fit a sixteenth of the shared memory, so that
+            // sixteen warps stay resident per CTA.
+            int const max_words = (int)((12 * 1024) / ((size_t)model.scoring.n_classes * 32 * 4));
             int words = 0, lanes = 0;
-            myers_shape_for_length(length, words, lanes);
-            // One warp's match table must fit a sixteenth of the shared memory, so sixteen warps stay resident.
-            bool const fits = words > 0 && (size_t)model.scoring.n_classes * 32 * words * 4 <= 12 * 1024;
-            if (!fits) {
+            myers_shape_for_length(length, max_words, words, lanes);
+            if (words == 0) {
                 kept.push_back(c);
                 continue;
             }
@@ -664,6 +683,14 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         by_length.swap(kept);
     }
     size_t const n_dp_candidates = by_length.size();
+    // Heaviest launch first, so that the lighter ones fill the tail of the heavier ones.
+    auto launch_weight = [&](MyersLaunch const &launch) {
+        uint64_t weight = 0;
+        for (MyersCandidate const &member : launch.members) weight += candidate_length(member.candidate);
+        return weight;
+    };
+    std::sort(myers_launches.begin(), myers_launches.end(),
+              [&](MyersLaunch const &a, MyersLaunch const &b) { return launch_weight(a) > launch_weight(b); });
 
     struct HostSlot {
         CandSlot slot;
@@ -775,7 +802,9 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     }
     SZB_CUDA(cudaMemsetAsync(engine.counters.ptr, 0, (plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64, stream));
     SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
-    if (scratch_words_per_cta) SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms));
+    // Launches overlap on side streams: every plan gets its own per-CTA boundary scratch.
+    if (scratch_words_per_cta)
+        SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms * plans.size()));
 
     // 7a. The bit-parallel launches' candidate lists.
     std::vector<MyersCandidate> myers_flat;
@@ -790,6 +819,17 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
 
     // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
     SZB_CUDA(cudaEventRecord(engine.events[1], stream));
+    size_t const n_launches = myers_launches.size() + plans.size();
+    bool const fan_out = n_launches > 1;
+    size_t launch_ordinal = 0;
+    auto next_stream = [&]() -> cudaStream_t {
+        size_t const slot = launch_ordinal++ % (Engine::kSideStreams + 1);
+        return (fan_out && slot) ? engine.side_streams[slot - 1] : stream;
+    };
+    if (fan_out) {
+        SZB_CUDA(cudaEventRecord(engine.fork_event, stream));
+        for (cudaStream_t side : engine.side_streams) SZB_CUDA(cudaStreamWaitEvent(side, engine.fork_event, 0));
+    }
     {
         size_t first = 0;
         for (size_t l = 0; l < myers_launches.size(); ++l) {
@@ -823,7 +863,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             args.row_base = (uint32_t)row_begin;
             uint64_t const tasks = blocks * launch.members.size();
             int const grid = (int)std::min<uint64_t>((tasks + warps - 1) / warps, (uint64_t)device_sms * ctas_per_sm);
-            SZB_CUDA(launch_myers(launch.words, grid, kThreads, smem, stream, args));
+            SZB_CUDA(launch_myers(launch.words, grid, kThreads, smem, next_stream(), args));
             stats.kernel_launches++;
             first += launch.members.size();
         }
@@ -842,13 +882,18 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         args.results = engine.results.as<int64_t>();
         args.stride = n_candidates;
         args.row_base = (uint32_t)row_begin;
-        args.scratch = engine.scratch.as<uint32_t>();
+        args.scratch = engine.scratch.as<uint32_t>() + p * scratch_words_per_cta * (uint64_t)device_sms;
         args.scratch_words_per_cta = scratch_words_per_cta;
         int const grid = (int)std::min<uint32_t>(plan.n_jobs, (uint32_t)device_sms);
         size_t const smem = shared_bytes(plan.widest_coverage, model.scoring.n_classes, model.scoring.compare != 0);
-        SZB_CUDA(launch_wavefront(plan.family, plan.strip_index, grid, smem, stream, args));
+        SZB_CUDA(launch_wavefront(plan.family, plan.strip_index, grid, smem, next_stream(), args));
         stats.kernel_launches++;
     }
+    if (fan_out)
+        for (int i = 0; i < Engine::kSideStreams; ++i) {
+            SZB_CUDA(cudaEventRecord(engine.join_events[i], engine.side_streams[i]));
+            SZB_CUDA(cudaStreamWaitEvent(stream, engine.join_events[i], 0));
+        }
     if (symmetric && whole_matrix && n_queries > 1) {
         uint64_t const total = (uint64_t)n_queries * n_queries;
         int const blocks = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);

@@ -30,7 +30,9 @@ cudaError_t launch_myers(int words, int grid, int threads, size_t smem, cudaStre
     case 5: return launch_words<5>(grid, threads, smem, stream, args);
     case 6: return launch_words<6>(grid, threads, smem, stream, args);
     case 7: return launch_words<7>(grid, threads, smem, stream, args);
-    default: return launch_words<8>(grid, threads, smem, stream, args);
+    case 8: return launch_words<8>(grid, threads, smem, stream, args);
+    case 9: return launch_words<9>(grid, threads, smem, stream, args);
+    default: return launch_words<10>(grid, threads, smem, stream, args);
     }
 }
 

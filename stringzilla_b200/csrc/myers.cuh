@@ -16,7 +16,8 @@
  *      Xv = Eq | Mv;  sum = (Eq & Pv) + Pv + carry;  Xh = (sum ^ Pv) | Eq;
  *      Ph = Mv | ~(Xh | Pv);  Mh = Pv & Xh;  Ph' = (Ph << 1) | ph_in;  Mh' = (Mh << 1) | mh_in;
  *      Pv = Mh' | ~(Xv | Ph');  Mv = Ph' & Xv
- *  = 7 LOP3 + 2 SHF + 1 IADD3.X per 32 DP cells. The distance is read off the final vertical deltas:
+ *  = 7 LOP3 + 1 IADD3.X per 32 DP cells plus two 1-bit shifts, which alternate between SHF (ALU pipe) and
+ *  IMAD / IMAD.HI (FMA pipe) from word to word. The distance is read off the final vertical deltas:
  *      D(m, n) = n + popc(Pv & mask_m) - popc(Mv & mask_m),
  *  so no per-step score tracking exists. `Eq` comes from a per-warp match table in shared memory,
  *  peq[class][word-in-lane][lane], built with `__ballot_sync` from the candidate's class bytes and replicated for the
@@ -60,11 +61,14 @@ struct MyersArgs {
  *  @tparam W 32-bit pattern words per lane; a group of G lanes covers 32 * W * G pattern characters.
  */
 template <int W>
-__global__ void __launch_bounds__(kThreads) myers_kernel(MyersArgs const args) {
+__global__ void __launch_bounds__(kThreads, 2) myers_kernel(MyersArgs const args) {
     extern __shared__ __align__(16) uint32_t smem[];
     constexpr int ROW = 32 * W; // words per class row: [word-in-lane][lane]
     int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int const n_classes = args.n_classes;
+    // Multipliers the compiler cannot see through, so that the shifts below stay integer multiply-adds.
+    uint32_t two;
+    asm volatile("mov.u32 %0, 2;" : "=r"(two));
     uint32_t *const peq = smem + (size_t)warp * n_classes * ROW;
 
     for (;;) {
@@ -128,13 +132,13 @@ __global__ void __launch_bounds__(kThreads) myers_kernel(MyersArgs const args) {
             bool valid_next = gl == 0 && n > 0;
             for (int s = 0; s < steps; ++s) {
                 uint32_t in = __shfl_up_sync(0xFFFFFFFFu, out, 1, G);
-                if (gl == 0) in = 0x80000000u; // row 0 of the DP: D(0, j) - D(0, j - 1) = +1
+                if (gl == 0) in = 0x80000000u; // row 0 of the DP: D(0, j) - D(0, j - 1) = +1, i.e. a Ph carry
                 bool const valid = valid_next;
                 uint32_t const a = a_next;
-                {   // Prefetch the class of the next text character of this lane (clamped, always in bounds).
+                {   // Prefetch the class of the next text character of this lane.
                     int const next = s + 1 - gl;
                     valid_next = (unsigned)next < (unsigned)n;
-                    a_next = q_ptr[min(max(next, 0), max(n - 1, 0))];
+                    if (valid_next) a_next = q_ptr[next];
                 }
                 if (valid) {
                     uint32_t const *const row = peq + a * ROW + lane;
@@ -142,6 +146,9 @@ __global__ void __launch_bounds__(kThreads) myers_kernel(MyersArgs const args) {
 #pragma unroll
                     for (int w = 0; w < W; ++w) eq[w] = row[w * 32], t[w] = eq[w] & pv[w];
                     uint32_t const carry = add_carry_chain<W>(sum, t, pv, in & 1u);
+                    // The 1-bit left shifts of Ph and Mh alternate between the two integer pipes: even words use a
+                    // funnel shift (ALU pipe), odd words `x * 2 + carry` with the carry from `hi(x * 2)` (IMAD and
+                    // IMAD.HI on the FMA pipe), which keeps both pipes busy without saturating either.
                     uint32_t ph_below = in, mh_below = in << 1; // only bit 31 of each is consumed
 #pragma unroll
                     for (int w = 0; w < W; ++w) {
@@ -149,8 +156,18 @@ __global__ void __launch_bounds__(kThreads) myers_kernel(MyersArgs const args) {
                         uint32_t const ph = mv[w] | ~(xh | pv[w]);
                         uint32_t const mh = pv[w] & xh;
                         uint32_t const xv = eq[w] | mv[w];
-                        uint32_t const ph_shifted = __funnelshift_l(ph_below, ph, 1);
-                        uint32_t const mh_shifted = __funnelshift_l(mh_below, mh, 1);
+                        uint32_t ph_shifted, mh_shifted;
+                        if (w & 1) {
+                            uint32_t ph_carry, mh_carry;
+                            asm("mul.hi.u32 %0, %1, %2;" : "=r"(ph_carry) : "r"(ph_below), "r"(two));
+                            asm("mul.hi.u32 %0, %1, %2;" : "=r"(mh_carry) : "r"(mh_below), "r"(two));
+                            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(ph_shifted) : "r"(ph), "r"(two), "r"(ph_carry));
+                            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(mh_shifted) : "r"(mh), "r"(two), "r"(mh_carry));
+                        }
+                        else {
+                            ph_shifted = __funnelshift_l(ph_below, ph, 1);
+                            mh_shifted = __funnelshift_l(mh_below, mh, 1);
+                        }
                         ph_below = ph, mh_below = mh;
                         pv[w] = mh_shifted | ~(xv | ph_shifted);
                         mv[w] = ph_shifted & xv;
@@ -170,14 +187,14 @@ __global__ void __launch_bounds__(kThreads) myers_kernel(MyersArgs const args) {
     }
 }
 
-constexpr int kMyersMaxWords = 8;
+constexpr int kMyersMaxWords = 10; // two 512-thread CTAs per SM need <= 64 registers per thread
 
-/** Picks (W, G) with the tightest coverage 32 * W * G >= pattern length; returns W = 0 when nothing fits. */
-inline void myers_shape_for_length(uint32_t length, int &words, int &lanes) {
+/** Picks (W <= max_words, G) with the tightest coverage 32 * W * G >= pattern length; W = 0 when nothing fits. */
+inline void myers_shape_for_length(uint32_t length, int max_words, int &words, int &lanes) {
     words = 0, lanes = 0;
     uint32_t best = 0xFFFFFFFFu;
-    for (int g = 8; g <= 32; g *= 2)
-        for (int w = 1; w <= kMyersMaxWords; ++w) {
+    for (int g = 1; g <= 32; g *= 2)
+        for (int w = 1; w <= kMyersMaxWords && w <= max_words; ++w) {
             uint32_t const coverage = 32u * w * g;
             if (coverage < length) continue;
             // Ties go to more words per lane: fewer lanes per query means more queries per warp and less overhead.

@@ -72,15 +72,16 @@ def test_bit_parallel_levenshtein_shapes(scope):
     """Every (words per lane, lanes) shape of the bit-parallel kernel: pattern lengths 0..9000 (longer ones fall back to
     the DP tiers), ragged text lengths, a 21-letter alphabet, and the engine statistics proving which kernel ran."""
     rng = np.random.default_rng(29)
-    lengths = [0, 1, 31, 32, 33, 255, 256, 257, 511, 513, 767, 769, 1023, 1024, 1025, 1279, 1281, 1535, 1537, 1791,
-               1793, 2047, 2049, 3071, 3073, 4095, 4097, 5000, 6143, 6145, 7167, 7169, 8191, 8192, 8193, 9000]
+    lengths = [0, 1, 31, 32, 33, 63, 65, 100, 129, 255, 256, 257, 511, 513, 767, 769, 1023, 1024, 1025, 1279, 1281,
+               1535, 1537, 1791, 1793, 2047, 2049, 3071, 3073, 4095, 4097, 5000, 6143, 6145, 7167, 7169, 8191, 8192,
+               8193, 9000, 12289, 16383, 16384, 16385, 17000]
     candidates = [support.random_strings(rng, 1, n, n, support.DNA)[0] for n in lengths]
     queries = support.random_strings(rng, 5, 0, 3000, support.DNA) + [b"", candidates[17][::-1], candidates[9]]
     engine = szb.LevenshteinDistances()
     got = engine(queries, candidates, device=scope)
     assert np.array_equal(got, support.oracle_levenshtein(queries, candidates))
     stats = engine.last_call_stats
-    assert stats.pairs_bit_parallel > 0 and stats.pairs_u16 > 0  # 8193 and 9000 exceed the widest bit-parallel shape
+    assert stats.pairs_bit_parallel > 0 and stats.pairs_u16 > 0  # 16385 and 17000 exceed the widest bit-parallel shape
     proteins = support.random_strings(rng, 9, 0, 700, support.PROTEIN)
     others = support.mutated_copies(rng, proteins, 0.2, support.PROTEIN) + support.random_strings(rng, 7, 0, 1500, support.PROTEIN)
     engine = szb.LevenshteinDistances()
