@@ -702,11 +702,11 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     uint64_t cells_total = 0, cells_u16 = 0;
     uint64_t query_bytes_in_rows = 0;
     for (uint32_t q : order) query_bytes_in_rows += query_length(q);
-    // Affine recurrences keep two register strips per lane: cap their strip width at 32 columns to stay spill-free.
+    // Affine recurrences keep two register strips per lane: cap their strip width at 36 columns (128 registers).
     auto shape_of = [&](int family, uint32_t longest) {
         Shape shape = shape_for_length(longest);
-        if (family_is_affine(family) && kStrips[shape.strip_index] > 32) {
-            uint32_t const passes = (longest + 1023) / 1024, width = (longest + passes - 1) / passes;
+        if (family_is_affine(family) && kStrips[shape.strip_index] > 36) {
+            uint32_t const passes = (longest + 1151) / 1152, width = (longest + passes - 1) / passes;
             for (int i = 0; i < kStripCount; ++i)
                 if ((uint32_t)kStrips[i] * 32 >= width) return Shape {i, 32};
         }
@@ -885,7 +885,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         args.scratch = engine.scratch.as<uint32_t>() + p * scratch_words_per_cta * (uint64_t)device_sms;
         args.scratch_words_per_cta = scratch_words_per_cta;
         int const grid = (int)std::min<uint32_t>(plan.n_jobs, (uint32_t)device_sms);
-        size_t const smem = shared_bytes(plan.widest_coverage, model.scoring.n_classes, model.scoring.compare != 0);
+        size_t const smem = shared_bytes(plan.strip_index, model.scoring.n_classes, model.scoring.compare != 0);
         SZB_CUDA(launch_wavefront(plan.family, plan.strip_index, grid, smem, next_stream(), args));
         stats.kernel_launches++;
     }

@@ -244,6 +244,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
     for (int offset = 16; offset >= G; offset >>= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, offset));
 
     uint32_t a_next = (gl == 0 && m > 0) ? q_ptr[0] : 0;
+    bool valid_next = gl == 0 && m > 0;
     uint32_t bw_next = 0, be_next = 0;
     if constexpr (MULTI) {
         if (from_scratch && m > 0) {
@@ -251,12 +252,11 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
             if constexpr (affine) be_next = bnd[per_row + 1];
         }
     }
-    uint4 const *const strip_profile = (uint4 const *)prof + gl;
+    // Shared-window byte address of this lane's slot in profile row 0; a row is K / 4 vectors of 32 slots x 16 bytes.
+    uint32_t const strip_address = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)gl * 16u;
+    constexpr uint32_t row_bytes = (uint32_t)K * 32u * 4u;
 
     for (int s = 0; s < steps; ++s) {
-        int const r = s - gl + 1; // DP row processed in this step
-        bool const valid = r >= 1 && r <= m;
-
         // Strip's left neighbour: the last cell of the lane to the left, one step ago.
         uint32_t w_in = __shfl_up_sync(0xFFFFFFFFu, w_out, 1, G);
         uint32_t e_in = 0;
@@ -265,20 +265,21 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
             if (!MULTI || pass == 0) {
                 if constexpr (packed) { w_in = left_boundary, e_in = left_gap_boundary; }
                 else {
-                    w_in = (uint32_t)(int)degenerate_score<FAM>(r, open, extend);
+                    w_in = (uint32_t)(int)degenerate_score<FAM>(s + 1, open, extend); // DP row r = s + 1 on lane 0
                     if constexpr (affine) e_in = w_in + (uint32_t)(open + extend);
                 }
             }
             else { w_in = bw_next, e_in = be_next; }
         }
 
+        bool const valid = valid_next; // this lane processes DP row r = s - gl + 1 in this step
         uint32_t const a = a_next;
         {   // Prefetch the next row's class and (multi-pass) boundary cell.
             int const next = s + 1 - gl;
-            bool const has_next = next >= 0 && next < m;
-            a_next = has_next ? q_ptr[next] : 0;
+            valid_next = (unsigned)next < (unsigned)m;
+            if (valid_next) a_next = q_ptr[next];
             if constexpr (MULTI) {
-                if (from_scratch && has_next) {
+                if (from_scratch && valid_next) {
                     bw_next = bnd[(next + 1) * per_row];
                     if constexpr (affine) be_next = bnd[(next + 1) * per_row + 1];
                 }
@@ -287,15 +288,15 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
 
         if (valid) {
             uint32_t d = diag_in, l = w_in, e = e_in;
-            uint4 const *prow = strip_profile + (size_t)a * (COLS / 4);
+            uint32_t const row_address = strip_address + a * row_bytes;
             int const a_int = (int)a;
 #pragma unroll
             for (int v = 0; v < VECS; ++v) {
                 uint32_t p[4];
                 if (!compare) {
-                    uint4 const pv = *prow;
-                    prow += G;
-                    p[0] = pv.x, p[1] = pv.y, p[2] = pv.z, p[3] = pv.w;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3])
+                                 : "r"(row_address + (uint32_t)v * 512u));
                 }
                 else {
                     if constexpr (!packed) {
@@ -305,41 +306,35 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                                                                                               : sc.cmp_mismatch);
                     }
                 }
+                // The four diagonal terms of this vector depend only on the previous row: form them before the
+                // cells of the current row overwrite the strip.
+                uint32_t t4[4];
+                t4[0] = d + p[0], t4[1] = h[v * 4] + p[1], t4[2] = h[v * 4 + 1] + p[2], t4[3] = h[v * 4 + 2] + p[3];
+                d = h[v * 4 + 3];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     int const k = v * 4 + i;
-                    if constexpr (FAM == FAM_LIN_SHIFT) {
-                        uint32_t const t = d + p[i];
-                        d = h[k];
-                        l = h[k] = __vimax3_u16x2(t, h[k], l);
-                    }
+                    if constexpr (FAM == FAM_LIN_SHIFT) { l = h[k] = __vimax3_u16x2(t4[i], h[k], l); }
                     else if constexpr (FAM == FAM_AFF_SHIFT) {
-                        uint32_t const t = d + p[i];
-                        d = h[k];
                         f[k] = __viaddmax_u16x2(h[k], sc.neg_go_bits, f[k]);
                         e = __viaddmax_u16x2(l, sc.neg_go_bits, e);
-                        l = h[k] = __vimax3_u16x2(t, f[k], e);
+                        l = h[k] = __vimax3_u16x2(t4[i], f[k], e);
                     }
                     else if constexpr (FAM == FAM_SW_LIN) {
-                        uint32_t const t = d + p[i];
                         uint32_t const up_gap = h[k] + sc.gap_arith;
-                        d = h[k];
-                        uint32_t const x = __vimax3_u16x2(t, up_gap, sc.bias_bits);
+                        uint32_t const x = __vimax3_u16x2(t4[i], up_gap, sc.bias_bits);
                         l = h[k] = __viaddmax_u16x2(l, sc.gap_bits, x);
                         if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
                     }
                     else if constexpr (FAM == FAM_SW_AFF) {
-                        uint32_t const t = d + p[i];
-                        d = h[k];
                         f[k] = __viaddmax_u16x2(h[k], sc.gap_bits, f[k] + sc.ext_arith);
                         e = __viaddmax_u16x2(l, sc.gap_bits, e + sc.ext_arith);
-                        uint32_t const x = __vimax3_u16x2(t, f[k], sc.bias_bits);
+                        uint32_t const x = __vimax3_u16x2(t4[i], f[k], sc.bias_bits);
                         l = h[k] = __vmaxu2(x, e);
                         if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
                     }
                     else { // signed 32-bit cells, literal recurrences
-                        int const t = (int)d + (int)p[i];
-                        d = h[k];
+                        int const t = (int)t4[i];
                         int score;
                         if constexpr (affine) {
                             int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
@@ -361,6 +356,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
             w_out = l, e_out = e;
             if constexpr (MULTI) {
                 if (to_scratch) {
+                    int const r = s - gl + 1; // the DP row just finished
                     bnd[r * per_row] = l;
                     if constexpr (affine) bnd[r * per_row + 1] = e;
                 }
@@ -435,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     int const n_classes = sc_global->n_classes;
     uint32_t *const ctl = smem;                // [0] job index, [1] next batch
     int8_t *const sub = (int8_t *)(smem + 4);  // 1024 B
-    uint32_t *const prof = smem + 4 + 256;     // [n_classes][K * G], vector-interleaved; unused in compare mode
+    uint32_t *const prof = smem + 4 + 256;     // [n_classes][K / 4][32 slots][4]; unused in compare mode
 
     SweepConstants sc;
     sc.open = sc_global->open, sc.extend = sc_global->extend, sc.bias = sc_global->bias;
@@ -479,9 +475,11 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
                     int const b0 = v0 ? c0_ptr[col] : 0, b1 = v1 ? c1_ptr[col] : 0;
                     int const e0 = profile_term<FAM>(sub, a, b0, v0, sc.open, sc.extend, sc.bias);
                     int const e1 = profile_term<FAM>(sub, a, b1, v1, sc.open, sc.extend, sc.bias);
+                    // Row layout: [vector v = k / 4][strip slot, 32 per vector][4 words]; a strip is one lane's K
+                    // columns, so lane `gl` reads its v-th vector at the compile-time offset v * 512 bytes.
                     int const strip = j / K, k = j - strip * K;
-                    int const word = ((k / 4) * G + strip) * 4 + (k % 4);
-                    prof[a * COLS + word] = packed ? pack_arith(e0, e1) : (uint32_t)e0;
+                    int const word = ((k / 4) * 32 + strip) * 4 + (k % 4);
+                    prof[a * (K * 32) + word] = packed ? pack_arith(e0, e1) : (uint32_t)e0;
                 }
             }
             __syncthreads();

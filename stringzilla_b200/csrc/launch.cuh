@@ -44,9 +44,10 @@ inline Shape shape_for_length(uint32_t longest) {
     return best;
 }
 
-/** Dynamic shared memory of one CTA: two control words, the 32x32 table, and the profile of the widest job. */
-inline size_t shared_bytes(int coverage, int n_classes, bool compare) {
-    size_t const profile = compare ? 0 : (size_t)n_classes * coverage * 4;
+/** Dynamic shared memory of one CTA: two control words, the 32x32 table, and the profile: per class K / 4 vectors
+ *  of 32 strip slots x 16 bytes (the slot count is fixed so that vector offsets are compile-time constants). */
+inline size_t shared_bytes(int strip_index, int n_classes, bool compare) {
+    size_t const profile = compare ? 0 : (size_t)n_classes * kStrips[strip_index] * 32 * 4;
     return 16 + 1024 + profile;
 }
 
