@@ -319,9 +319,7 @@ def run_ours(args):
         # Rank 0 owns the host inputs: H2D there, one NCCL broadcast, row-sharded scoring, one NCCL gather, D2H.
         q_tape = q if rank == 0 else None
         c_tape = c if rank == 0 else None
-        qd, qo = sharding.broadcast_tape(q_tape, src=0, device=device)
-        cd, co = sharding.broadcast_tape(c_tape, src=0, device=device)
-        qo_host, co_host = qo.cpu().numpy().astype(np.uint64), co.cpu().numpy().astype(np.uint64)
+        (qd, qo_host), (cd, co_host) = sharding.broadcast_tapes([q_tape, c_tape], src=0, device=device)
         ltq = _abi.SequenceU64Tape(qd.data_ptr(), qo_host.ctypes.data, len(qo_host) - 1)
         ltc = _abi.SequenceU64Tape(cd.data_ptr(), co_host.ctypes.data, len(co_host) - 1)
         _abi.check(lib.szs_b200_scores_u64tape_rows(engine._family_index, engine._handle, scope.handle, ct.byref(ltq),

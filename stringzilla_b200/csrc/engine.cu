@@ -74,6 +74,19 @@ __global__ void mirror_lower_kernel(int64_t *results, uint64_t n, uint64_t strid
     }
 }
 
+/**
+ *  Symmetric mode with symmetric costs: only cells (query q, candidate c) with position[q] <= position[c] in the
+ *  longest-first query order were scored (each unordered pair once, the longer string as the query); fill the rest.
+ */
+__global__ void mirror_ranked_kernel(int64_t *results, uint64_t n, uint64_t stride, uint32_t const *position) {
+    uint64_t const total = n * n;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t const i = idx / n, j = idx % n;
+        if (position[i] > position[j]) results[i * stride + j] = results[j * stride + i];
+    }
+}
+
 #pragma endregion
 
 #pragma region Errors
@@ -263,7 +276,7 @@ struct Engine {
 
     // Grow-only device state, one set per engine: engines are not re-entrant.
     StagedSet queries, candidates;
-    DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch, myers_candidates;
+    DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch, myers_candidates, positions;
     PinnedBuffer upload, upload_model;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     // Independent launches of one call (different strip widths, word counts, families) overlap their tails on side
@@ -642,6 +655,18 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return query_length(a) > query_length(b); });
     uint32_t const longest_query = query_length(order[0]);
 
+    // Symmetric self-similarity under a symmetric cost model: score every unordered pair once, with the string that
+    // comes first in the longest-first order as the query. A candidate at position p then needs only the queries at
+    // positions [0, p] — a prefix of the order — and a ranked mirror fills the other half. (An asymmetric substitution
+    // table must follow the reference's (query = i, candidate = j <= i) orientation: full matrix + index mirror.)
+    bool const triangle = symmetric && whole_matrix && model.symmetric_costs && n_queries > 1;
+    std::vector<uint32_t> position;
+    if (triangle) {
+        position.resize(n_queries);
+        for (uint32_t p = 0; p < (uint32_t)n_rows; ++p) position[order[p]] = p;
+    }
+    auto rows_needed = [&](uint32_t candidate) { return triangle ? position[candidate] + 1 : (uint32_t)n_rows; };
+
     // 5. Slots: candidates sorted by length; neighbours share a register in the packed tier.
     std::vector<uint32_t> by_length(n_candidates);
     std::iota(by_length.begin(), by_length.end(), 0u);
@@ -676,7 +701,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             auto launch = std::find_if(myers_launches.begin(), myers_launches.end(),
                                        [&](MyersLaunch const &l) { return l.words == words; });
             if (launch == myers_launches.end()) myers_launches.push_back({words, {}}), launch = myers_launches.end() - 1;
-            launch->members.push_back({c, (uint32_t)lanes});
+            launch->members.push_back({c, (uint32_t)lanes, rows_needed(c)});
             cells_myers += (uint64_t)length * query_bytes;
         }
         std::reverse(kept.begin(), kept.end()); // back to ascending length for the slot builder
@@ -755,12 +780,14 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
                 // A block is a whole number of rounds of the CTA's warps (each sweeps 32 / G queries at a time),
                 // so that no warp idles at the job's barrier while others run an extra round.
                 uint32_t const round = (uint32_t)(kThreads / 32) * (32 / shape.lanes);
-                uint64_t const rounds_total = (n_rows + round - 1) / round;
+                uint32_t const slot_rows =
+                    std::max(rows_needed(slot.c0), slot.c1 != kNoCandidate ? rows_needed(slot.c1) : 0u);
+                uint64_t const rounds_total = (slot_rows + round - 1) / round;
                 uint64_t const blocks = std::max<uint64_t>(1, std::min<uint64_t>(wanted_blocks, rounds_total));
                 uint32_t const block_rows = (uint32_t)((rounds_total + blocks - 1) / blocks) * round;
                 uint32_t const longest = std::max(slot.len0, slot.len1);
-                for (uint32_t begin = 0; begin < n_rows; begin += block_rows) {
-                    uint32_t const end = (uint32_t)std::min<uint64_t>(n_rows, (uint64_t)begin + block_rows);
+                for (uint32_t begin = 0; begin < slot_rows; begin += block_rows) {
+                    uint32_t const end = (uint32_t)std::min<uint64_t>(slot_rows, (uint64_t)begin + block_rows);
                     if (longest > (uint32_t)shape.coverage()) {
                         uint64_t const rows = (uint64_t)query_length(order[begin]) + 1;
                         uint64_t const words = (uint64_t)(end - begin) * rows * (affine ? 2 : 1);
@@ -815,6 +842,14 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
                                  cudaMemcpyHostToDevice, stream));
         SZB_CUDA(cudaStreamSynchronize(stream)); // `myers_flat` is pageable and local
         stats.h2d_bytes += myers_flat.size() * sizeof(MyersCandidate);
+    }
+
+    if (triangle) {
+        SZB_CUDA(engine.positions.reserve(position.size() * sizeof(uint32_t)));
+        SZB_CUDA(cudaMemcpyAsync(engine.positions.ptr, position.data(), position.size() * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream)); // `position` is pageable and local
+        stats.h2d_bytes += position.size() * sizeof(uint32_t);
     }
 
     // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
@@ -897,7 +932,11 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     if (symmetric && whole_matrix && n_queries > 1) {
         uint64_t const total = (uint64_t)n_queries * n_queries;
         int const blocks = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);
-        mirror_lower_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates);
+        if (triangle)
+            mirror_ranked_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates,
+                                                             engine.positions.as<uint32_t>());
+        else
+            mirror_lower_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates);
         SZB_CUDA(cudaGetLastError());
         stats.kernel_launches++;
     }

@@ -58,6 +58,49 @@ def broadcast_tape(tape, src: int = 0, device=None, group=None):
     return data, offsets
 
 
+def broadcast_tapes(tapes, src: int = 0, device=None, group=None):
+    """Broadcasts several `Tape`s from `src` as ONE payload (plus one small header): offsets first (8-byte aligned),
+    then the byte blobs. Non-source ranks pass `None` entries. Returns a list of (data_tensor, offsets_numpy_uint64):
+    the blobs stay on `device` (views into the received payload), the offsets come back to the host in one copy,
+    because the C ABI reads them there."""
+    import torch
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    backend_device = device if device is not None else torch.device("cpu")
+    count = len(tapes)
+    header = torch.zeros(2 * count, dtype=torch.int64, device=backend_device)
+    if rank == src:
+        for i, tape in enumerate(tapes):
+            header[2 * i], header[2 * i + 1] = int(tape.offsets.size), int(tape.data.size)
+    dist.broadcast(header, src=src, group=group)
+    sizes = header.cpu().tolist()
+    offsets_bytes = sum(8 * sizes[2 * i] for i in range(count))
+    total = offsets_bytes + sum(sizes[2 * i + 1] for i in range(count))
+    if rank == src:
+        host = np.empty(total, dtype=np.uint8)
+        cursor = 0
+        for tape in tapes:
+            chunk = tape.offsets.astype(np.uint64).view(np.uint8)
+            host[cursor : cursor + chunk.size] = chunk
+            cursor += chunk.size
+        for tape in tapes:
+            host[cursor : cursor + tape.data.size] = tape.data
+            cursor += tape.data.size
+        payload = torch.from_numpy(host).to(backend_device)
+    else:
+        payload = torch.empty(total, dtype=torch.uint8, device=backend_device)
+    dist.broadcast(payload, src=src, group=group)
+    all_offsets = payload[:offsets_bytes].cpu().numpy().view(np.uint64)
+    out, offsets_cursor, data_cursor = [], 0, offsets_bytes
+    for i in range(count):
+        n_offsets, n_bytes = sizes[2 * i], sizes[2 * i + 1]
+        out.append((payload[data_cursor : data_cursor + n_bytes], all_offsets[offsets_cursor : offsets_cursor + n_offsets].copy()))
+        offsets_cursor += n_offsets
+        data_cursor += n_bytes
+    return out
+
+
 def gather_rows(local_rows, blocks: list[tuple[int, int]], n_columns: int, dst: int = 0, group=None):
     """Gathers each rank's contiguous (rows_block x n_columns) score slab on `dst`; returns the full matrix there
     (a torch tensor on the slabs' device) and None elsewhere. Slabs are padded to the tallest block so that one

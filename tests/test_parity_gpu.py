@@ -153,6 +153,23 @@ def test_symmetric_self_similarity(scope):
         assert np.array_equal(got, support.oracle_weighted(proteins, None, byte_to_class, costs, -4, -1, local))
 
 
+def test_symmetric_triangle_scheduling(scope):
+    """Symmetric calls under symmetric costs score each unordered pair once (longer string as the query) and mirror by
+    rank; equal lengths, empties, multi-pass lengths and both Levenshtein kernels must all survive that."""
+    rng = np.random.default_rng(31)
+    strings = (support.random_strings(rng, 30, 0, 400, support.DNA) + [b"", b"", b"ACGT" * 50, b"ACGT" * 50]
+               + support.random_strings(rng, 6, 1400, 3000, support.DNA))
+    for costs, kwargs in (((0, 1, 1, 1), {}), ((0, 1, 1, 1), {"bit_parallel": False}), ((1, 3, 4, 2), {})):
+        got = szb.LevenshteinDistances(*costs, **kwargs)(strings, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(strings, None, *costs))
+    byte_to_class, costs = scoring.blosum62()
+    proteins = support.random_strings(rng, 25, 0, 500, support.PROTEIN) + support.random_strings(rng, 3, 1300, 2500, support.PROTEIN)
+    for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+        for gaps in ((-4, -4), (-4, -1)):
+            got = engine_type(byte_to_class, costs, open=gaps[0], extend=gaps[1])(proteins, device=scope)
+            assert np.array_equal(got, support.oracle_weighted(proteins, None, byte_to_class, costs, *gaps, local))
+
+
 def test_asymmetric_substitution_table(scope):
     """cost[class(query)][class(candidate)] — the query indexes the row (SURVEY §7 'hard parts')."""
     rng = np.random.default_rng(8)

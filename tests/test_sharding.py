@@ -45,10 +45,14 @@ def _worker(rank: int, world: int, port: int, seed: int):
         candidates = support.random_strings(rng, 9, 0, 120, support.DNA)
         q_tape = szb.Tape(queries) if rank == 0 else None
         c_tape = szb.Tape(candidates) if rank == 0 else None
-        q_data, q_off = sharding.broadcast_tape(q_tape)
-        c_data, c_off = sharding.broadcast_tape(c_tape)
-        q_local = szb.Tape((q_data.numpy(), q_off.numpy().astype(np.uint64)))
-        c_local = szb.Tape((c_data.numpy(), c_off.numpy().astype(np.uint64)))
+        if seed % 2:
+            (q_data, q_off), (c_data, c_off) = sharding.broadcast_tapes([q_tape, c_tape])
+            q_local, c_local = szb.Tape((q_data.numpy(), q_off)), szb.Tape((c_data.numpy(), c_off))
+        else:
+            q_data, q_off = sharding.broadcast_tape(q_tape)
+            c_data, c_off = sharding.broadcast_tape(c_tape)
+            q_local = szb.Tape((q_data.numpy(), q_off.numpy().astype(np.uint64)))
+            c_local = szb.Tape((c_data.numpy(), c_off.numpy().astype(np.uint64)))
 
         def score_rows(begin, end):
             rows = [q_local[i] for i in range(begin, end)]
@@ -64,7 +68,8 @@ def _worker(rank: int, world: int, port: int, seed: int):
         dist.destroy_process_group()
 
 
-def test_broadcast_shard_gather_with_gloo_world_size_2():
+@pytest.mark.parametrize("seed", [98, 99], ids=["per_tape_broadcasts", "packed_broadcast"])
+def test_broadcast_shard_gather_with_gloo_world_size_2(seed):
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(2, _free_port(), 99), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), seed), nprocs=2, join=True)
