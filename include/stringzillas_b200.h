@@ -172,8 +172,10 @@ SZS_B200_API sz_status_t szs_levenshtein_distances_u64tape(szs_levenshtein_dista
                                                            char const **error_message);
 SZS_B200_API void szs_levenshtein_distances_free(szs_levenshtein_distances_t engine);
 
-/* ---- UTF-8 Levenshtein (reference stringzillas.h:256-328). OUT OF SCOPE for this hot path:
- *      the symbols exist so that bindings resolve; `_init` reports `sz_missing_gpu_k`. ---------------------------- */
+/* ---- UTF-8 Levenshtein (reference stringzillas.h:256-328, c/stringzillas/levenshtein.cuh:247-371): edit distance over
+ *      UTF-8 runes. Strings are decoded with the reference's unchecked rule (utf8_runes/serial.h:111-124); pure-ASCII
+ *      input takes the byte-level kernels, anything else the 32-bit-symbol compare recurrences. Unlike the reference's
+ *      CUDA backend, custom and affine gap costs are supported. --------------------------------------------------- */
 
 typedef void *szs_levenshtein_distances_utf8_t;
 SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_init(sz_error_cost_t match, sz_error_cost_t mismatch,

@@ -23,6 +23,8 @@
  *   cross product / symmetric ... serial.hpp:3140-3187 (lower triangle incl. diagonal, scored as (query=i, cand=j<=i)
  *                                  and mirrored), include/stringzillas/stringzillas.h:173-177
  *   substitution lookup ......... serial.hpp:193-200: cost = table[byte_to_class[q]][byte_to_class[c]] (query = row)
+ *   UTF-8 Levenshtein ........... serial.hpp:2796-2898: both strings are transcoded to UTF-32 with the UNCHECKED decoder
+ *                                  (include/stringzilla/utf8_runes/serial.h:111-124) and the same recurrences run over runes
  *
  * Arithmetic: Levenshtein accumulates in unsigned 64-bit exactly like the baselines' std::size_t (the int8 costs are
  * converted as the C++ baselines convert them); NW/SW accumulate in signed 64-bit (std::ptrdiff_t).
@@ -227,6 +229,101 @@ ORACLE_API int oracle_weighted_cross(uint8_t const *q_data, uint64_t const *q_of
             }
         }
         free(scratch);
+    }
+    return 0;
+}
+
+/* ---- UTF-8 Levenshtein: the same recurrences over runes -------------------------------------------------------------- */
+
+/* include/stringzilla/utf8_runes/serial.h:111-124 — the lead byte alone decides the length; no validation. Bytes past
+ * the end read as zero here (the reference over-reads; well-formed input never gets there). */
+static size_t decode_utf8(uint8_t const *text, size_t length, uint32_t *runes) {
+    size_t produced = 0;
+    for (size_t i = 0; i < length;) {
+        uint32_t lead = text[i];
+        size_t n = 1 + (lead >= 0xC0U) + (lead >= 0xE0U) + (lead >= 0xF0U);
+        uint32_t b1 = i + 1 < length ? text[i + 1] : 0, b2 = i + 2 < length ? text[i + 2] : 0,
+                 b3 = i + 3 < length ? text[i + 3] : 0;
+        uint32_t rune;
+        if (n == 1) rune = lead;
+        else if (n == 2) rune = (lead & 0x1FU) << 6 | (b1 & 0x3FU);
+        else if (n == 3) rune = (lead & 0x0FU) << 12 | (b1 & 0x3FU) << 6 | (b2 & 0x3FU);
+        else rune = (lead & 0x07U) << 18 | (b1 & 0x3FU) << 12 | (b2 & 0x3FU) << 6 | (b3 & 0x3FU);
+        runes[produced++] = rune;
+        i += n;
+    }
+    return produced;
+}
+
+static uint64_t levenshtein_runes(uint32_t const *s1, size_t len1, uint32_t const *s2, size_t len2, int8_t match,
+                                  int8_t mismatch, int8_t open, int8_t extend, uint64_t *scratch) {
+    size_t const cols = len2 + 1;
+    uint64_t const o = (uint64_t)(int64_t)open, e = (uint64_t)(int64_t)extend;
+    if (open == extend) { /* test/similarities.cuh:47-70 over runes */
+        uint64_t *previous = scratch, *current = scratch + cols;
+        for (size_t j = 0; j < cols; ++j) previous[j] = (uint64_t)j * o;
+        for (size_t i = 1; i <= len1; ++i) {
+            current[0] = (uint64_t)i * o;
+            for (size_t j = 1; j < cols; ++j) {
+                uint64_t substitution = (uint64_t)(int64_t)(s1[i - 1] == s2[j - 1] ? match : mismatch);
+                current[j] = min_u64(min_u64(previous[j], current[j - 1]) + o, previous[j - 1] + substitution);
+            }
+            uint64_t *t = previous;
+            previous = current, current = t;
+        }
+        return previous[cols - 1];
+    }
+    /* test/similarities.cuh:136-180 over runes */
+    uint64_t *ps = scratch, *cs = scratch + cols, *pi = scratch + 2 * cols, *ci = scratch + 3 * cols,
+             *pd = scratch + 4 * cols, *cd = scratch + 5 * cols;
+    memset(scratch, 0, sizeof(uint64_t) * 6 * cols);
+    for (size_t j = 1; j < cols; ++j) ps[j] = o + (uint64_t)(j - 1) * e, pd[j] = ps[j] + o + e;
+    for (size_t i = 1; i <= len1; ++i) {
+        cs[0] = o + (uint64_t)(i - 1) * e;
+        ci[0] = cs[0] + o + e;
+        for (size_t j = 1; j < cols; ++j) {
+            uint64_t substitution = (uint64_t)(int64_t)(s1[i - 1] == s2[j - 1] ? match : mismatch);
+            uint64_t if_insertion = min_u64(cs[j - 1] + o, ci[j - 1] + e);
+            uint64_t if_deletion = min_u64(ps[j] + o, pd[j] + e);
+            cs[j] = min_u64(min_u64(if_deletion, if_insertion), ps[j - 1] + substitution);
+            ci[j] = if_insertion, cd[j] = if_deletion;
+        }
+        uint64_t *t;
+        t = ps, ps = cs, cs = t;
+        t = pi, pi = ci, ci = t;
+        t = pd, pd = cd, cd = t;
+    }
+    return ps[cols - 1];
+}
+
+ORACLE_API int oracle_levenshtein_utf8_cross(uint8_t const *q_data, uint64_t const *q_off, size_t q_count,
+                                             uint8_t const *c_data, uint64_t const *c_off, size_t c_count,
+                                             int8_t match, int8_t mismatch, int8_t open, int8_t extend,
+                                             uint64_t *results, size_t row_stride) {
+    int const symmetric = c_data == NULL;
+    if (symmetric) c_data = q_data, c_off = q_off, c_count = q_count;
+    size_t longest_q = 0, longest_c = 0;
+    for (size_t i = 0; i < q_count; ++i)
+        if (q_off[i + 1] - q_off[i] > longest_q) longest_q = q_off[i + 1] - q_off[i];
+    for (size_t j = 0; j < c_count; ++j)
+        if (c_off[j + 1] - c_off[j] > longest_c) longest_c = c_off[j + 1] - c_off[j];
+#pragma omp parallel
+    {
+        uint64_t *scratch = (uint64_t *)malloc(sizeof(uint64_t) * 6 * (longest_c + 1));
+        uint32_t *qr = (uint32_t *)malloc(sizeof(uint32_t) * (longest_q + 1));
+        uint32_t *cr = (uint32_t *)malloc(sizeof(uint32_t) * (longest_c + 1));
+#pragma omp for schedule(dynamic, 1)
+        for (long long i = 0; i < (long long)q_count; ++i) {
+            size_t const nq = decode_utf8(q_data + q_off[i], q_off[i + 1] - q_off[i], qr);
+            size_t const end = symmetric ? (size_t)i + 1 : c_count;
+            for (size_t j = 0; j < end; ++j) {
+                size_t const nc = decode_utf8(c_data + c_off[j], c_off[j + 1] - c_off[j], cr);
+                uint64_t r = levenshtein_runes(qr, nq, cr, nc, match, mismatch, open, extend, scratch);
+                results[(size_t)i * row_stride + j] = r;
+                if (symmetric && j != (size_t)i) results[j * row_stride + (size_t)i] = r;
+            }
+        }
+        free(scratch), free(qr), free(cr);
     }
     return 0;
 }

@@ -20,6 +20,7 @@ from ._abi import CallStats, SimilarityError  # noqa: F401  (re-exported)
 __all__ = [
     "DeviceScope",
     "LevenshteinDistances",
+    "LevenshteinDistancesUTF8",
     "NeedlemanWunschScores",
     "SmithWatermanScores",
     "Tape",
@@ -215,6 +216,23 @@ class LevenshteinDistances(_Engine):
         _abi.check(status, message)
         if not bit_parallel:
             self._lib.szs_b200_set_bit_parallel(self._handle, 0)
+
+
+class LevenshteinDistancesUTF8(_Engine):
+    """Mirror of `stringzillas.LevenshteinDistancesUTF8(match=0, mismatch=1, open=1, extend=1, capabilities=...)`
+    (python/stringzillas/similarities.c:519-547): edit distance over UTF-8 runes instead of bytes."""
+
+    _family = "levenshtein_distances_utf8"
+    _result_dtype = np.uint64
+
+    def __init__(self, match: int = 0, mismatch: int = 1, open: int = 1, extend: int = 1, capabilities=None,
+                 library_path=None):  # fmt: skip
+        super().__init__(library_path)
+        message = ct.c_char_p()
+        status = self._lib.szs_levenshtein_distances_utf8_init(
+            match, mismatch, open, extend, None, _resolve_capabilities(capabilities, self._lib),
+            ct.byref(self._handle), ct.byref(message))  # fmt: skip
+        _abi.check(status, message)
 
 
 class _Weighted(_Engine):

@@ -147,9 +147,11 @@ def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
     lib.szs_device_scope_free.restype = None
 
     lib.szs_levenshtein_distances_init.argtypes = [i8, i8, i8, i8, vp, ct.c_uint32, ct.POINTER(vp), err]
+    lib.szs_levenshtein_distances_utf8_init.argtypes = [i8, i8, i8, i8, vp, ct.c_uint32, ct.POINTER(vp), err]
     for family in ("szs_needleman_wunsch_scores", "szs_smith_waterman_scores"):
         getattr(lib, family + "_init").argtypes = [vp, vp, i8, i8, vp, ct.c_uint32, ct.POINTER(vp), err]
-    for family in ("szs_levenshtein_distances", "szs_needleman_wunsch_scores", "szs_smith_waterman_scores"):
+    for family in ("szs_levenshtein_distances", "szs_levenshtein_distances_utf8", "szs_needleman_wunsch_scores",
+                   "szs_smith_waterman_scores"):
         for suffix in ("", "_u32tape", "_u64tape"):
             getattr(lib, family + suffix).argtypes = [vp, vp, vp, vp, vp, u64, err]
             getattr(lib, family + suffix).restype = ct.c_int

@@ -87,6 +87,38 @@ __global__ void mirror_ranked_kernel(int64_t *results, uint64_t n, uint64_t stri
     }
 }
 
+/**
+ *  UTF-8 -> UTF-32, one thread per string, with the reference's UNCHECKED decoding rule
+ *  (include/stringzilla/utf8_runes/serial.h:111-124): the lead byte alone decides the sequence length
+ *  (1 + (lead >= 0xC0) + (lead >= 0xE0) + (lead >= 0xF0)); bytes past the end of the string read as zero.
+ *  `runes == nullptr` only counts.
+ */
+__global__ void utf8_decode_kernel(uint8_t const *bytes, uint32_t const *byte_offsets, uint32_t n_strings,
+                                   uint32_t *counts, uint32_t const *rune_offsets, uint32_t *runes) {
+    uint32_t const index = blockIdx.x * blockDim.x + threadIdx.x;
+    if (index >= n_strings) return;
+    uint32_t const begin = byte_offsets[index], end = byte_offsets[index + 1];
+    uint32_t produced = 0;
+    uint32_t *const out = runes ? runes + rune_offsets[index] : nullptr;
+    for (uint32_t i = begin; i < end;) {
+        uint32_t const lead = bytes[i];
+        uint32_t const length = 1u + (lead >= 0xC0u) + (lead >= 0xE0u) + (lead >= 0xF0u);
+        if (out) {
+            uint32_t const b1 = i + 1 < end ? bytes[i + 1] : 0, b2 = i + 2 < end ? bytes[i + 2] : 0,
+                           b3 = i + 3 < end ? bytes[i + 3] : 0;
+            uint32_t rune;
+            if (length == 1) rune = lead;
+            else if (length == 2) rune = (lead & 0x1Fu) << 6 | (b1 & 0x3Fu);
+            else if (length == 3) rune = (lead & 0x0Fu) << 12 | (b1 & 0x3Fu) << 6 | (b2 & 0x3Fu);
+            else rune = (lead & 0x07u) << 18 | (b1 & 0x3Fu) << 12 | (b2 & 0x3Fu) << 6 | (b3 & 0x3Fu);
+            out[produced] = rune;
+        }
+        ++produced;
+        i += length;
+    }
+    if (counts) counts[index] = produced;
+}
+
 #pragma endregion
 
 #pragma region Errors
@@ -256,6 +288,8 @@ struct StagedSet {
     std::vector<uint32_t> offsets; // count + 1, relative to the staged blob
     uint32_t longest = 0;
     DeviceBuffer raw, classes, device_offsets;
+    DeviceBuffer rune_counts, rune_offsets, runes; // UTF-8 engines: the decoded symbol streams
+    std::vector<uint32_t> rune_counts_host;
     PinnedBuffer gather; // only for callback sequences
     std::vector<uint8_t> offsets_bounce;
 };
@@ -273,10 +307,11 @@ struct Engine {
     uint8_t byte_to_class[256] = {0};
     int8_t costs[32 * 32] = {0};
     bool bit_parallel = true; // unit-cost Levenshtein may take the bit-parallel kernel (szs_b200_set_bit_parallel)
+    bool utf8 = false;        // Levenshtein over UTF-8 runes instead of bytes (szs_levenshtein_distances_utf8*)
 
     // Grow-only device state, one set per engine: engines are not re-entrant.
     StagedSet queries, candidates;
-    DeviceBuffer results, scoring, lut, flags, slots, jobs, order, counters, scratch, myers_candidates, positions;
+    DeviceBuffer results, scoring, lut, flags, query_flags, slots, jobs, order, counters, scratch, myers_candidates, positions;
     PinnedBuffer upload, upload_model;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     // Independent launches of one call (different strip widths, word counts, families) overlap their tails on side
@@ -433,7 +468,7 @@ struct Model {
  *  Translates the engine's costs into the kernels' maximising convention and decides which recurrence families
  *  are exact for them. `present` flags the byte values occurring among the candidates (Levenshtein only).
  */
-static void build_model(Engine const &engine, uint32_t const *present, Model &model) {
+static void build_model(Engine const &engine, uint32_t const *present, bool wide_symbols, Model &model) {
     Scoring &sc = model.scoring;
     std::memset(&sc, 0, sizeof(sc));
     bool const local = engine.algorithm == Algorithm::kSmithWaterman;
@@ -447,7 +482,7 @@ static void build_model(Engine const &engine, uint32_t const *present, Model &mo
         sc.match = -engine.match, sc.mismatch = -engine.mismatch;
         int distinct = 0;
         for (int b = 0; b < 256; ++b) distinct += present[b] != 0;
-        if (distinct <= 31) {
+        if (distinct <= 31 && !wide_symbols) {
             int next = 0;
             for (int b = 0; b < 256; ++b) model.lut[b] = present[b] ? (uint8_t)next++ : (uint8_t)distinct;
             sc.n_classes = distinct + 1; // the last class collects query bytes no candidate contains
@@ -599,6 +634,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
 
     // 2. The scoring model; Levenshtein compacts the alphabet of the candidates into <= 31 classes.
     uint32_t present[256] = {0};
+    bool wide_symbols = false;
     if (engine.algorithm == Algorithm::kLevenshtein) {
         SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
         SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
@@ -608,12 +644,73 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             SZB_CUDA(cudaGetLastError());
             stats.kernel_launches++;
         }
+        uint32_t query_present[256] = {0};
+        if (engine.utf8 && !symmetric && qs.total_bytes) {
+            SZB_CUDA(engine.query_flags.reserve(256 * sizeof(uint32_t)));
+            SZB_CUDA(cudaMemsetAsync(engine.query_flags.ptr, 0, 256 * sizeof(uint32_t), stream));
+            byte_presence_kernel<<<296, 512, 0, stream>>>(qs.raw.as<uint8_t>(), qs.total_bytes,
+                                                          engine.query_flags.as<uint32_t>());
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
+            SZB_CUDA(cudaMemcpyAsync(query_present, engine.query_flags.ptr, sizeof(query_present),
+                                     cudaMemcpyDeviceToHost, stream));
+            stats.d2h_bytes += sizeof(query_present);
+        }
         SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
         SZB_CUDA(cudaStreamSynchronize(stream));
         stats.d2h_bytes += sizeof(present);
+        if (engine.utf8)
+            for (int b = 128; b < 256; ++b) wide_symbols |= present[b] != 0 || query_present[b] != 0;
+    }
+
+    // 2a. UTF-8 engines: pure-ASCII input is byte-level Levenshtein (as the reference's per-pair ASCII fallback,
+    //     serial.hpp:2811-2814); anything else is decoded into UTF-32 symbol streams that replace the byte streams
+    //     in everything downstream (lengths, offsets, scheduling), and scored by the symbol-compare recurrences.
+    if (wide_symbols) {
+        auto decode_set = [&](StagedSet &set) -> Failure {
+            uint32_t const count = (uint32_t)set.count;
+            SZB_CUDA(set.rune_counts.reserve((size_t)(count + 1) * sizeof(uint32_t)));
+            SZB_CUDA(set.rune_offsets.reserve((size_t)(count + 1) * sizeof(uint32_t)));
+            int const blocks = (int)((count + 127) / 128);
+            if (count) {
+                utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
+                                                               count, set.rune_counts.as<uint32_t>(), nullptr, nullptr);
+                SZB_CUDA(cudaGetLastError());
+                stats.kernel_launches++;
+            }
+            set.rune_counts_host.resize(count + 1);
+            SZB_CUDA(cudaMemcpyAsync(set.rune_counts_host.data(), set.rune_counts.ptr, (size_t)count * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, stream));
+            SZB_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += (size_t)count * sizeof(uint32_t);
+            uint64_t running = 0;
+            set.longest = 0;
+            for (uint32_t i = 0; i < count; ++i) {
+                uint32_t const runes = set.rune_counts_host[i];
+                set.offsets[i] = (uint32_t)running; // from here on, offsets and lengths are in symbols
+                running += runes;
+                set.longest = std::max(set.longest, runes);
+            }
+            set.offsets[count] = (uint32_t)running;
+            SZB_CUDA(cudaMemcpyAsync(set.rune_offsets.ptr, set.offsets.data(), (size_t)(count + 1) * sizeof(uint32_t),
+                                     cudaMemcpyHostToDevice, stream));
+            SZB_CUDA(set.runes.reserve((running + 64) * sizeof(uint32_t)));
+            if (count) {
+                utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
+                                                               count, nullptr, set.rune_offsets.as<uint32_t>(),
+                                                               set.runes.as<uint32_t>());
+                SZB_CUDA(cudaGetLastError());
+                stats.kernel_launches++;
+            }
+            SZB_CUDA(cudaStreamSynchronize(stream)); // `set.offsets` must not change while the copy is in flight
+            return ok();
+        };
+        if (Failure failure = decode_set(qs)) return failure;
+        if (!symmetric)
+            if (Failure failure = decode_set(cs)) return failure;
     }
     Model model;
-    build_model(engine, present, model);
+    build_model(engine, present, wide_symbols, model);
     if (!fits_s32(engine, (uint64_t)qs.longest + cs.longest))
         return fail(sz_overflow_risk_k, "Pair too long for 32-bit DP cells");
 
@@ -630,6 +727,11 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
 
     // 3. Bytes -> classes (skipped in compare mode, where the kernels read raw bytes).
     uint8_t const *q_classes = qs.raw.as<uint8_t>(), *c_classes = cs.raw.as<uint8_t>();
+    uint32_t const *q_offsets = qs.device_offsets.as<uint32_t>(), *c_offsets = cs.device_offsets.as<uint32_t>();
+    if (wide_symbols) {
+        q_classes = qs.runes.as<uint8_t>(), c_classes = cs.runes.as<uint8_t>();
+        q_offsets = qs.rune_offsets.as<uint32_t>(), c_offsets = cs.rune_offsets.as<uint32_t>();
+    }
     if (!model.scoring.compare) {
         auto map_set = [&](StagedSet &set) -> Failure {
             if (!set.total_bytes) return ok();
@@ -727,11 +829,18 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     uint64_t cells_total = 0, cells_u16 = 0;
     uint64_t query_bytes_in_rows = 0;
     for (uint32_t q : order) query_bytes_in_rows += query_length(q);
-    // Affine recurrences keep two register strips per lane: cap their strip width at 36 columns (128 registers).
+    // Register budget (128 per thread) caps the strip width per family: packed affine recurrences keep two strips per
+    // lane (36 columns), the 32-bit tier adds the strip's symbols for compare mode (32 linear / 20 affine).
+    auto widest_strip = [](int family) {
+        if (family >= FAM_S32_GLOBAL_LIN) return family_is_affine(family) ? 20 : 32;
+        return family_is_affine(family) ? 36 : 40;
+    };
     auto shape_of = [&](int family, uint32_t longest) {
         Shape shape = shape_for_length(longest);
-        if (family_is_affine(family) && kStrips[shape.strip_index] > 36) {
-            uint32_t const passes = (longest + 1151) / 1152, width = (longest + passes - 1) / passes;
+        int const cap = widest_strip(family);
+        if (kStrips[shape.strip_index] > cap) {
+            uint32_t const widest = (uint32_t)cap * 32;
+            uint32_t const passes = (longest + widest - 1) / widest, width = (longest + passes - 1) / passes;
             for (int i = 0; i < kStripCount; ++i)
                 if ((uint32_t)kStrips[i] * 32 >= width) return Shape {i, 32};
         }
@@ -883,8 +992,8 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             uint64_t const blocks = (sweeps_per_candidate + batches_per_block - 1) / batches_per_block;
             if (blocks * launch.members.size() > 0xFFFFFFF0ull) return fail(sz_overflow_risk_k, "Too many tasks");
             MyersArgs args;
-            args.q_cls = q_classes, args.q_off = qs.device_offsets.as<uint32_t>();
-            args.c_cls = c_classes, args.c_off = cs.device_offsets.as<uint32_t>();
+            args.q_cls = q_classes, args.q_off = q_offsets;
+            args.c_cls = c_classes, args.c_off = c_offsets;
             args.q_order = engine.order.as<uint32_t>();
             args.candidates = engine.myers_candidates.as<MyersCandidate>() + first;
             args.n_candidates = (uint32_t)launch.members.size();
@@ -906,8 +1015,9 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     for (size_t p = 0; p < plans.size(); ++p) {
         LaunchPlan const &plan = plans[p];
         KernelArgs args;
-        args.q_cls = q_classes, args.q_off = qs.device_offsets.as<uint32_t>();
-        args.c_cls = c_classes, args.c_off = cs.device_offsets.as<uint32_t>();
+        args.q_cls = q_classes, args.q_off = q_offsets;
+        args.c_cls = c_classes, args.c_off = c_offsets;
+        args.wide_symbols = wide_symbols ? 1u : 0u;
         args.q_order = engine.order.as<uint32_t>();
         args.slots = engine.slots.as<CandSlot>();
         args.jobs = engine.jobs.as<Job>() + plan.first_job;
@@ -1123,6 +1233,19 @@ SZS_B200_API sz_status_t szs_levenshtein_distances_init(sz_error_cost_t match, s
     return status;
 }
 
+SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_init(sz_error_cost_t match, sz_error_cost_t mismatch,
+                                                             sz_error_cost_t open, sz_error_cost_t extend,
+                                                             sz_memory_allocator_t const *, sz_capability_t,
+                                                             szs_levenshtein_distances_utf8_t *engine,
+                                                             char const **error_message) {
+    Engine *made = nullptr;
+    sz_status_t status = make_engine(szb::Algorithm::kLevenshtein, engine, error_message, &made);
+    if (status != sz_success_k) return status;
+    made->match = match, made->mismatch = mismatch, made->open = open, made->extend = extend;
+    made->utf8 = true;
+    return status;
+}
+
 static sz_status_t init_weighted(szb::Algorithm algorithm, sz_u8_t const *byte_to_class,
                                  sz_error_cost_t const *class_substitution_costs, sz_error_cost_t open,
                                  sz_error_cost_t extend, void **engine, char const **error_message) {
@@ -1194,39 +1317,15 @@ static sz_status_t run(void *engine, szb::Algorithm expected, szs_device_scope_t
     SZS_B200_API void name##_free(void *engine) { delete static_cast<Engine *>(engine); }
 
 SZB_DEFINE_CALLS(szs_levenshtein_distances, szb::Algorithm::kLevenshtein, sz_size_t)
+SZB_DEFINE_CALLS(szs_levenshtein_distances_utf8, szb::Algorithm::kLevenshtein, sz_size_t)
 SZB_DEFINE_CALLS(szs_needleman_wunsch_scores, szb::Algorithm::kNeedlemanWunsch, sz_ssize_t)
 SZB_DEFINE_CALLS(szs_smith_waterman_scores, szb::Algorithm::kSmithWaterman, sz_ssize_t)
 
-/* ---- Out-of-scope families: present so that bindings resolve, refusing loudly (no CPU fallback). ---------------- */
+/* ---- Out-of-scope family (fingerprints): present so that bindings resolve, refusing loudly (no CPU fallback). ---- */
 
 static sz_status_t out_of_scope(char const **error_message) {
     return szb::report(szb::fail(sz_missing_gpu_k, "Not part of the stringzillas_b200 hot path"), error_message);
 }
-
-SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_init(sz_error_cost_t, sz_error_cost_t, sz_error_cost_t,
-                                                             sz_error_cost_t, sz_memory_allocator_t const *,
-                                                             sz_capability_t, szs_levenshtein_distances_utf8_t *,
-                                                             char const **error_message) {
-    return out_of_scope(error_message);
-}
-SZS_B200_API sz_status_t szs_levenshtein_distances_utf8(szs_levenshtein_distances_utf8_t, szs_device_scope_t,
-                                                        sz_sequence_t const *, sz_sequence_t const *, sz_size_t *,
-                                                        sz_size_t, char const **error_message) {
-    return out_of_scope(error_message);
-}
-SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_u32tape(szs_levenshtein_distances_utf8_t, szs_device_scope_t,
-                                                                sz_sequence_u32tape_t const *,
-                                                                sz_sequence_u32tape_t const *, sz_size_t *, sz_size_t,
-                                                                char const **error_message) {
-    return out_of_scope(error_message);
-}
-SZS_B200_API sz_status_t szs_levenshtein_distances_utf8_u64tape(szs_levenshtein_distances_utf8_t, szs_device_scope_t,
-                                                                sz_sequence_u64tape_t const *,
-                                                                sz_sequence_u64tape_t const *, sz_size_t *, sz_size_t,
-                                                                char const **error_message) {
-    return out_of_scope(error_message);
-}
-SZS_B200_API void szs_levenshtein_distances_utf8_free(szs_levenshtein_distances_utf8_t) {}
 
 SZS_B200_API sz_status_t szs_fingerprints_init(sz_size_t, sz_size_t, sz_size_t const *, sz_size_t, sz_u64_t,
                                                sz_memory_allocator_t const *, sz_capability_t, szs_fingerprints_t *,

@@ -101,6 +101,7 @@ struct KernelArgs {
     uint32_t row_base;
     uint32_t *scratch;       ///< per-CTA multi-pass boundary storage
     uint64_t scratch_words_per_cta;
+    uint32_t wide_symbols;   ///< compare mode only: q_cls / c_cls are uint32 symbol streams (UTF-8 runes), offsets in symbols
 };
 
 __device__ __forceinline__ uint32_t pack_arith(int lo, int hi) { return (uint32_t)(hi * 65536 + lo); }
@@ -189,7 +190,9 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
 
     // Top boundary: DP row 0 of the strip, and the seeds of the gap tracks.
     uint32_t h[K], f[affine ? K : 1];
-    uint32_t cb[(!packed) ? VECS : 1]; // compare mode: the strip's raw candidate bytes
+    uint32_t cb[(!packed) ? K : 1]; // compare mode: the strip's candidate symbols (bytes, or runes when wide)
+    bool const wide = !packed && args.wide_symbols != 0;
+    uint32_t const *const q_wide = (uint32_t const *)args.q_cls + q_begin_off;
     uint32_t diag_in, w_out = 0, e_out = 0, best = 0;
     uint32_t left_boundary = 0, left_gap_boundary = 0; // pass 0, lane 0: DP column 0 (packed families: constant)
     if constexpr (FAM == FAM_LIN_SHIFT) {
@@ -224,17 +227,14 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         }
         diag_in = (uint32_t)(int)degenerate_score<FAM>(cbase, open, extend);
         if (compare) {
+            uint32_t const c_begin_off = args.c_off[slot.c0];
 #pragma unroll
-            for (int v = 0; v < VECS; ++v) {
-                uint32_t word = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t const col = (uint32_t)cbase + v * 4 + i;
-                    // Padding columns compare against byte 0; their cells are never read.
-                    uint32_t const byte = col < slot.len0 ? c0_ptr[col] : 0u;
-                    word |= (byte & 0xFFu) << (8 * i);
-                }
-                cb[v] = word;
+            for (int k = 0; k < K; ++k) {
+                uint32_t const col = (uint32_t)cbase + k;
+                // Padding columns hold a symbol no string contains; their cells are never read anyway.
+                cb[k] = col >= slot.len0 ? 0xFFFFFFFFu
+                        : wide           ? ((uint32_t const *)args.c_cls)[c_begin_off + col]
+                                         : (uint32_t)c0_ptr[col];
             }
         }
     }
@@ -243,7 +243,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
     int steps = m > 0 ? m + G - 1 : 0;
     for (int offset = 16; offset >= G; offset >>= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, offset));
 
-    uint32_t a_next = (gl == 0 && m > 0) ? q_ptr[0] : 0;
+    uint32_t a_next = (gl == 0 && m > 0) ? (wide ? q_wide[0] : (uint32_t)q_ptr[0]) : 0;
     bool valid_next = gl == 0 && m > 0;
     uint32_t bw_next = 0, be_next = 0;
     if constexpr (MULTI) {
@@ -277,7 +277,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         {   // Prefetch the next row's class and (multi-pass) boundary cell.
             int const next = s + 1 - gl;
             valid_next = (unsigned)next < (unsigned)m;
-            if (valid_next) a_next = q_ptr[next];
+            if (valid_next) a_next = wide ? q_wide[next] : (uint32_t)q_ptr[next];
             if constexpr (MULTI) {
                 if (from_scratch && valid_next) {
                     bw_next = bnd[(next + 1) * per_row];
@@ -289,7 +289,6 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         if (valid) {
             uint32_t d = diag_in, l = w_in, e = e_in;
             uint32_t const row_address = strip_address + a * row_bytes;
-            int const a_int = (int)a;
 #pragma unroll
             for (int v = 0; v < VECS; ++v) {
                 uint32_t p[4];
@@ -302,8 +301,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                     if constexpr (!packed) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            p[i] = (uint32_t)(((cb[v] >> (8 * i)) & 0xFFu) == (uint32_t)a_int ? sc.cmp_match
-                                                                                              : sc.cmp_mismatch);
+                            p[i] = (uint32_t)(cb[v * 4 + i] == a ? sc.cmp_match : sc.cmp_mismatch);
                     }
                 }
                 // The four diagonal terms of this vector depend only on the previous row: form them before the

@@ -32,6 +32,8 @@ def run_reference(kind, queries, candidates, params):
     for caps in (_abi.CAP_SERIAL, szb.capabilities(REF)):
         if kind == "levenshtein":
             engine = szb.LevenshteinDistances(*params["costs"], capabilities=caps, library_path=REF)
+        elif kind == "levenshtein_utf8":
+            engine = szb.LevenshteinDistancesUTF8(*params["costs"], capabilities=caps, library_path=REF)
         else:
             engine_type = szb.NeedlemanWunschScores if kind == "needleman_wunsch" else szb.SmithWatermanScores
             engine = engine_type(np.array(params["byte_to_class"], dtype=np.uint8),
@@ -85,6 +87,23 @@ def main():
     text_c = ["the quick brown dog jumps over the lazy fox".encode(), "Zurich - Lodz - Aeroskobing".encode(),
               "naive cafe, jalapeno & pinata".encode(), "數據科學 321".encode(), b"\x00\x02\x01\xfe\xff binary!"]
     add("lev_unit_bytes_of_text", "levenshtein", text_q, text_c, costs=[0, 1, 1, 1])
+
+    # Rune-level distances: accents, combining marks, CJK, emoji, mixed scripts, plus pure ASCII (the byte fallback).
+    utf8_q = [t.encode() for t in ("αβγδ", "école", "Schön", "Data科学123", "🙂🌍🚀", "💖", "München", "façade", "こんにちは世界",
+                                   "plain ascii text", "", "naïve café, jalapeño & piñata", "Zürich — Łódź — Ærøskøbing",
+                                   "Ереван, თბილისი και Αθήνα – три столицы", "数据科学与机器学习" * 9)]
+    utf8_c = [t.encode() for t in ("αγδ", "e\u0301cole", "Scho\u0308n", "Data科學321", "🙂🌎✨", "💗", "Muenchen", "facade", "こんばんは世界",
+                                   "plain ascii texts", "ß", "naive cafe, jalapeno & pinata", "Zurich - Lodz - Aeroskobing",
+                                   "Երևան, თბილისი, και Αθήνα – 3 մայրաքաղաք", "數據科學與機器學習" * 8)]
+    add("lev_utf8_unit_mixed_scripts", "levenshtein_utf8", utf8_q, utf8_c, costs=[0, 1, 1, 1])
+    add("lev_utf8_affine_mixed_scripts", "levenshtein_utf8", utf8_q, utf8_c, costs=[0, 4, 3, 2])
+    add("lev_utf8_weird_linear_symmetric", "levenshtein_utf8", utf8_q, None, costs=[1, 3, 3, 3])
+    cyrillic = "абвгдежзийклмнопрстуфхцчшщъыьэюя "
+    ru_q = ["".join(cyrillic[i] for i in rng.integers(0, len(cyrillic), size=int(n))).encode() for n in rng.integers(0, 400, size=6)]
+    ru_c = support.mutated_copies(rng, [q.decode() for q in ru_q][:0], 0.0, b"") or [
+        "".join(cyrillic[i] for i in rng.integers(0, len(cyrillic), size=int(n))).encode() for n in rng.integers(1, 700, size=5)]
+    add("lev_utf8_unit_cyrillic_long", "levenshtein_utf8", ru_q, ru_c, costs=[0, 1, 1, 1])
+    add("lev_utf8_ascii_only", "levenshtein_utf8", dna_q, dna_c, costs=[0, 1, 1, 1])
 
     prot_q = support.random_strings(rng, 8, 0, 260, support.PROTEIN)
     prot_c = support.mutated_copies(rng, prot_q[:6], 0.25, support.PROTEIN) + support.random_strings(rng, 3, 1, 120, support.PROTEIN)

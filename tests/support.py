@@ -40,6 +40,7 @@ def oracle() -> ct.CDLL:
         lib.oracle_weighted.argtypes = [vp, u64, vp, u64, vp, vp, i8, i8, ct.c_int]
         lib.oracle_levenshtein_cross.argtypes = [vp, vp, u64, vp, vp, u64, i8, i8, i8, i8, vp, u64]
         lib.oracle_weighted_cross.argtypes = [vp, vp, u64, vp, vp, u64, vp, vp, i8, i8, ct.c_int, vp, u64]
+        lib.oracle_levenshtein_utf8_cross.argtypes = [vp, vp, u64, vp, vp, u64, i8, i8, i8, i8, vp, u64]
         _oracle = lib
     return _oracle
 
@@ -56,6 +57,18 @@ def oracle_levenshtein(queries, candidates=None, match=0, mismatch=1, open=1, ex
     cols = len(c) if c is not None else len(q)
     out = np.zeros((len(q), cols), dtype=np.uint64)
     oracle().oracle_levenshtein_cross(
+        q.data.ctypes.data, q.offsets.ctypes.data, len(q),
+        c.data.ctypes.data if c is not None else None, c.offsets.ctypes.data if c is not None else None, cols,
+        match, mismatch, open, extend, out.ctypes.data, max(cols, 1))  # fmt: skip
+    return out
+
+
+def oracle_levenshtein_utf8(queries, candidates=None, match=0, mismatch=1, open=1, extend=1) -> np.ndarray:
+    q = _tape(queries)
+    c = _tape(candidates) if candidates is not None else None
+    cols = len(c) if c is not None else len(q)
+    out = np.zeros((len(q), cols), dtype=np.uint64)
+    oracle().oracle_levenshtein_utf8_cross(
         q.data.ctypes.data, q.offsets.ctypes.data, len(q),
         c.data.ctypes.data if c is not None else None, c.offsets.ctypes.data if c is not None else None, cols,
         match, mismatch, open, extend, out.ctypes.data, max(cols, 1))  # fmt: skip

@@ -22,6 +22,8 @@ def oracle_for_case(case):
     params = case["params"]
     if case["kind"] == "levenshtein":
         return support.oracle_levenshtein(queries, candidates, *params["costs"]).astype(np.int64)
+    if case["kind"] == "levenshtein_utf8":
+        return support.oracle_levenshtein_utf8(queries, candidates, *params["costs"]).astype(np.int64)
     return support.oracle_weighted(
         queries, candidates, np.array(params["byte_to_class"], dtype=np.uint8),
         np.array(params["costs"], dtype=np.int8), params["open"], params["extend"],

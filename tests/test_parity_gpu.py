@@ -24,6 +24,8 @@ def scope():
 def engine_for(kind, params):
     if kind == "levenshtein":
         return szb.LevenshteinDistances(*params["costs"])
+    if kind == "levenshtein_utf8":
+        return szb.LevenshteinDistancesUTF8(*params["costs"])
     engine_type = szb.NeedlemanWunschScores if kind == "needleman_wunsch" else szb.SmithWatermanScores
     return engine_type(np.array(params["byte_to_class"], dtype=np.uint8),
                        np.array(params["costs"], dtype=np.int8).reshape(32, 32),
@@ -218,6 +220,36 @@ def test_unusual_cost_signs_take_the_literal_tier(scope):
             got = engine_type(byte_to_class, table, open=gaps[0], extend=gaps[1])(queries, candidates, device=scope)
             want = support.oracle_weighted(queries, candidates, byte_to_class, table, *gaps, local)
             assert np.array_equal(got, want), (engine_type.__name__, gaps)
+
+
+def test_utf8_levenshtein_rune_level(scope):
+    """Rune-level distances (reference test/similarities.py:231-260): accents, CJK, emoji; random multi-script text at
+    lengths that need several strip shapes; pure ASCII must equal the byte-level engine."""
+    engine = szb.LevenshteinDistancesUTF8()
+    distance = lambda a, b: int(engine([a.encode()], [b.encode()], device=scope)[0, 0])
+    assert distance("hello", "hell") == 1
+    assert distance("𠜎 𠜱 𠝹 𠱓", "𠜎𠜱𠝹𠱓") == 3
+    assert distance("💖", "💗") == 1
+    assert distance("αβγδ", "αγδ") == 1
+    assert distance("façade", "facade") == 1
+    assert distance("Schön", "Scho\u0308n") == 2
+    assert distance("こんにちは世界", "こんばんは世界") == 2
+    rng = np.random.default_rng(37)
+    alphabet = list("abcdefgh абвгдежз αβγδεζηθ 数据科学机器 🙂🌍🚀💖")
+    def text(n):
+        return "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=n)).encode()
+    queries = [text(int(n)) for n in rng.integers(0, 900, size=12)] + [b"", "é".encode()]
+    candidates = [text(int(n)) for n in rng.integers(0, 1500, size=9)] + [b"", b"plain"]
+    for costs in ((0, 1, 1, 1), (1, 3, 3, 3), (0, 4, 3, 2)):
+        got = szb.LevenshteinDistancesUTF8(*costs)(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, candidates, *costs)), costs
+    got = szb.LevenshteinDistancesUTF8()(queries, device=scope)
+    assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, None))
+    ascii_q = support.random_strings(rng, 8, 0, 300, b"abcdefghij ")
+    ascii_c = support.random_strings(rng, 7, 0, 300, b"abcdefghij ")
+    rune_level = szb.LevenshteinDistancesUTF8()
+    assert np.array_equal(rune_level(ascii_q, ascii_c, device=scope), support.oracle_levenshtein(ascii_q, ascii_c))
+    assert rune_level.last_call_stats.pairs_bit_parallel > 0  # pure ASCII takes the byte-level fast path
 
 
 def test_every_input_layout_of_the_abi(scope):
