@@ -785,15 +785,24 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     uint64_t cells_myers = 0;
     bool const unit_costs = engine.algorithm == Algorithm::kLevenshtein && engine.match == 0 && engine.mismatch == 1 &&
                             engine.open == 1 && engine.extend == 1;
-    if (unit_costs && engine.bit_parallel && !model.scoring.compare) {
+    // Compact alphabets keep one match table per WARP (rows = classes); raw-byte alphabets of more than 31 symbols keep
+    // one table per CTA whose rows are the bytes the candidate contains (bounded by the bytes any candidate contains).
+    bool const myers_shared_table = model.scoring.compare != 0;
+    int myers_rows = model.scoring.n_classes;
+    if (myers_shared_table) {
+        myers_rows = 1;
+        for (int b = 0; b < 256; ++b) myers_rows += present[b] != 0;
+    }
+    if (unit_costs && engine.bit_parallel && !wide_symbols) {
         uint64_t query_bytes = 0;
         for (uint32_t q : order) query_bytes += query_length(q);
         std::vector<uint32_t> kept;
+        // Shared memory bounds the words per lane: a sixteenth of the SM per warp-private table (sixteen resident
+        // warps per CTA), or the whole carve-out for a CTA-shared one.
+        size_t const table_budget = myers_shared_table ? 220 * 1024 - 1024 : 12 * 1024;
+        int const max_words = (int)(table_budget / ((size_t)myers_rows * 32 * 4));
         for (size_t i = n_candidates; i-- > 0;) { // longest first
             uint32_t const c = by_length[i], length = candidate_length(c);
-            // One warp's match table (classes x 32 x W words) must fit a sixteenth of the shared memory, so that
-            // sixteen warps stay resident per CTA.
-            int const max_words = (int)((12 * 1024) / ((size_t)model.scoring.n_classes * 32 * 4));
             int words = 0, lanes = 0;
             myers_shape_for_length(length, max_words, words, lanes);
             if (words == 0) {
@@ -978,17 +987,20 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         size_t first = 0;
         for (size_t l = 0; l < myers_launches.size(); ++l) {
             MyersLaunch const &launch = myers_launches[l];
-            size_t const table_bytes = (size_t)model.scoring.n_classes * 32 * launch.words * 4;
             int const warps = kThreads / 32;
-            size_t const smem = table_bytes * warps;
-            int const ctas_per_sm = smem * 2 <= 220 * 1024 ? 2 : 1;
-            int const resident_warps = device_sms * ctas_per_sm * warps;
-            // Enough tasks for ~16 per resident warp; a task is `batches_per_block` warp sweeps of one candidate.
+            size_t const smem = myers_shared_table
+                                    ? myers_shared_bytes(launch.words, myers_rows)
+                                    : (size_t)model.scoring.n_classes * 32 * launch.words * 4 * warps;
+            int const ctas_per_sm = (!myers_shared_table && smem * 2 <= 220 * 1024) ? 2 : 1;
+            // Work units that pull tasks: warps (private tables) or whole CTAs (shared table).
+            uint64_t const pullers = myers_shared_table ? (uint64_t)device_sms : (uint64_t)device_sms * ctas_per_sm * warps;
             uint32_t narrowest = 32;
             for (MyersCandidate const &member : launch.members) narrowest = std::min(narrowest, 32u / member.lanes);
             uint64_t const sweeps_per_candidate = (n_rows + narrowest - 1) / narrowest;
             uint64_t const total_sweeps = sweeps_per_candidate * launch.members.size();
-            uint64_t const batches_per_block = std::max<uint64_t>(1, total_sweeps / ((uint64_t)resident_warps * 16));
+            // ~16 tasks per puller; a shared-table task should also keep all sixteen warps busy for a few rounds.
+            uint64_t batches_per_block = std::max<uint64_t>(1, total_sweeps / (pullers * 16));
+            if (myers_shared_table) batches_per_block = std::max<uint64_t>(((batches_per_block + warps - 1) / warps) * warps, 2 * warps);
             uint64_t const blocks = (sweeps_per_candidate + batches_per_block - 1) / batches_per_block;
             if (blocks * launch.members.size() > 0xFFFFFFF0ull) return fail(sz_overflow_risk_k, "Too many tasks");
             MyersArgs args;
@@ -1006,8 +1018,10 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             args.stride = n_candidates;
             args.row_base = (uint32_t)row_begin;
             uint64_t const tasks = blocks * launch.members.size();
-            int const grid = (int)std::min<uint64_t>((tasks + warps - 1) / warps, (uint64_t)device_sms * ctas_per_sm);
-            SZB_CUDA(launch_myers(launch.words, grid, kThreads, smem, next_stream(), args));
+            int const grid = myers_shared_table
+                                 ? (int)std::min<uint64_t>(tasks, (uint64_t)device_sms)
+                                 : (int)std::min<uint64_t>((tasks + warps - 1) / warps, (uint64_t)device_sms * ctas_per_sm);
+            SZB_CUDA(launch_myers(launch.words, myers_shared_table, grid, kThreads, smem, next_stream(), args));
             stats.kernel_launches++;
             first += launch.members.size();
         }

@@ -1,14 +1,14 @@
 /**
  *  @file myers.cu
- *  @brief Instantiations of the bit-parallel unit-cost Levenshtein kernel, one per words-per-lane count.
+ *  @brief Instantiations of the bit-parallel unit-cost Levenshtein kernels, one per words-per-lane count.
  */
 #include "myers.cuh"
 
 namespace szb {
 
-template <int W>
+template <int W, bool SHARED>
 static cudaError_t launch_words(int grid, int threads, size_t smem, cudaStream_t stream, MyersArgs const &args) {
-    auto kernel = myers_kernel<W>;
+    auto kernel = SHARED ? myers_shared_kernel<W> : myers_kernel<W>;
     static bool configured[64] = {false};
     int device = 0;
     cudaGetDevice(&device);
@@ -21,19 +21,27 @@ static cudaError_t launch_words(int grid, int threads, size_t smem, cudaStream_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_myers(int words, int grid, int threads, size_t smem, cudaStream_t stream, MyersArgs const &args) {
+template <bool SHARED>
+static cudaError_t launch_variant(int words, int grid, int threads, size_t smem, cudaStream_t stream,
+                                  MyersArgs const &args) {
     switch (words) {
-    case 1: return launch_words<1>(grid, threads, smem, stream, args);
-    case 2: return launch_words<2>(grid, threads, smem, stream, args);
-    case 3: return launch_words<3>(grid, threads, smem, stream, args);
-    case 4: return launch_words<4>(grid, threads, smem, stream, args);
-    case 5: return launch_words<5>(grid, threads, smem, stream, args);
-    case 6: return launch_words<6>(grid, threads, smem, stream, args);
-    case 7: return launch_words<7>(grid, threads, smem, stream, args);
-    case 8: return launch_words<8>(grid, threads, smem, stream, args);
-    case 9: return launch_words<9>(grid, threads, smem, stream, args);
-    default: return launch_words<10>(grid, threads, smem, stream, args);
+    case 1: return launch_words<1, SHARED>(grid, threads, smem, stream, args);
+    case 2: return launch_words<2, SHARED>(grid, threads, smem, stream, args);
+    case 3: return launch_words<3, SHARED>(grid, threads, smem, stream, args);
+    case 4: return launch_words<4, SHARED>(grid, threads, smem, stream, args);
+    case 5: return launch_words<5, SHARED>(grid, threads, smem, stream, args);
+    case 6: return launch_words<6, SHARED>(grid, threads, smem, stream, args);
+    case 7: return launch_words<7, SHARED>(grid, threads, smem, stream, args);
+    case 8: return launch_words<8, SHARED>(grid, threads, smem, stream, args);
+    case 9: return launch_words<9, SHARED>(grid, threads, smem, stream, args);
+    default: return launch_words<10, SHARED>(grid, threads, smem, stream, args);
     }
+}
+
+cudaError_t launch_myers(int words, bool shared_table, int grid, int threads, size_t smem, cudaStream_t stream,
+                         MyersArgs const &args) {
+    return shared_table ? launch_variant<true>(words, grid, threads, smem, stream, args)
+                        : launch_variant<false>(words, grid, threads, smem, stream, args);
 }
 
 } // namespace szb

@@ -188,6 +188,23 @@ def test_asymmetric_substitution_table(scope):
         assert np.array_equal(got, support.oracle_weighted(queries, None, byte_to_class, costs, -2, -1, local))
 
 
+def test_bit_parallel_levenshtein_large_alphabets(scope):
+    """More than 31 distinct bytes: the CTA-shared match table ranks the bytes each candidate contains."""
+    rng = np.random.default_rng(41)
+    text = bytes(range(32, 127))
+    every_byte = bytes(range(256))
+    for alphabet, top in ((text, 1400), (every_byte, 900), (every_byte, 5000)):
+        lengths = [0, 1, 33, 200, 513, 1024, 1025, top]
+        candidates = [support.random_strings(rng, 1, n, n, alphabet)[0] for n in lengths]
+        queries = support.random_strings(rng, 21, 0, top, alphabet) + [b"", candidates[4], candidates[5][:-3] + b"xyz"]
+        engine = szb.LevenshteinDistances()
+        got = engine(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(queries, candidates))
+        assert engine.last_call_stats.pairs_bit_parallel > 0
+    strings = support.random_strings(rng, 40, 0, 300, text)
+    assert np.array_equal(szb.LevenshteinDistances()(strings, device=scope), support.oracle_levenshtein(strings, None))
+
+
 def test_large_alphabets_and_wide_cells(scope):
     """More than 31 distinct bytes -> byte-compare recurrences; high costs -> 32-bit cells (test/similarities.cuh:2023)."""
     rng = np.random.default_rng(13)
