@@ -78,6 +78,22 @@ def test_no_cpu_fallback(library_built):
         assert failure.value.status_name == "missing_gpu"
 
 
+@pytest.mark.skipif(not (support.ROOT.parent / "reference" / "include").is_dir() and not __import__("pathlib").Path("/root/reference/include").is_dir(),
+                    reason="the reference header tree exists only in the build container")
+def test_reference_header_compiles_and_links_against_our_library(library_built, tmp_path):
+    """The drop-in claim at source level: a C program written against the REFERENCE's stringzillas.h links against
+    libstringzillas_b200.so unchanged; without a GPU the scoring call must refuse (no CPU fallback)."""
+    import subprocess
+
+    binary = tmp_path / "dropin"
+    library_dir = support.ROOT / "stringzilla_b200" / "lib"
+    subprocess.run(["gcc", "-DSZ_DYNAMIC_DISPATCH=1", "-I/root/reference/include", str(support.ROOT / "tests" / "c_dropin_probe.c"),
+                    "-o", str(binary), f"-L{library_dir}", "-lstringzillas_b200", f"-Wl,-rpath,{library_dir}"], check=True)
+    ran = subprocess.run([str(binary)], capture_output=True, text=True)
+    assert ran.returncode == 0, ran.stdout + ran.stderr
+    assert "version 5.1.2" in ran.stdout
+
+
 def test_tape_packing():
     tape = szb.Tape([b"", b"abc", "é"])
     assert len(tape) == 3 and tape.offsets.tolist() == [0, 0, 3, 5]
