@@ -306,6 +306,61 @@ def test_every_input_layout_of_the_abi(scope):
     assert status == 0 and np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_differential(seed, scope):
+    """Seeded random configurations: family, costs (incl. unusual signs), alphabet size, length distribution, symmetric
+    or rectangular shape. Each seed draws several small tiles and compares every cell with the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    alphabets = [support.DNA, support.PROTEIN, bytes(range(97, 123)), bytes(range(32, 127)), bytes(range(256)), b"ab"]
+    for _ in range(6):
+        alphabet = alphabets[int(rng.integers(0, len(alphabets)))]
+        top = int(rng.choice([8, 40, 150, 400, 1300]))
+        n_q, n_c = int(rng.integers(1, 14)), int(rng.integers(1, 14))
+        queries = support.random_strings(rng, n_q, 0, top, alphabet)
+        symmetric = rng.random() < 0.25
+        if symmetric:
+            candidates = None
+        elif rng.random() < 0.5:
+            candidates = support.mutated_copies(rng, (queries * 3)[:n_c], 0.2, alphabet)
+        else:
+            candidates = support.random_strings(rng, n_c, 0, top, alphabet)
+        family = int(rng.integers(0, 3))
+        if family == 0:
+            match, mismatch = int(rng.integers(0, 3)), int(rng.integers(1, 9))
+            open_ = int(rng.integers(1, 9))
+            extend = open_ if rng.random() < 0.5 else int(rng.integers(1, 9))
+            got = szb.LevenshteinDistances(match, mismatch, open_, extend)(queries, candidates, device=scope)
+            want = support.oracle_levenshtein(queries, candidates, match, mismatch, open_, extend)
+            label = ("levenshtein", match, mismatch, open_, extend)
+        else:
+            n_symbols = min(len(alphabet), 31)
+            byte_to_class = np.zeros(256, dtype=np.uint8)
+            byte_to_class[np.frombuffer(alphabet, dtype=np.uint8)] = (np.arange(len(alphabet)) % n_symbols) + 1
+            costs = rng.integers(-9, 12, size=(32, 32)).astype(np.int8)
+            if rng.random() < 0.6:
+                costs = np.minimum(costs, costs.T)  # symmetric tables take the triangle path in symmetric calls
+            open_ = int(rng.integers(-12, 1)) if rng.random() < 0.85 else int(rng.integers(-3, 4))
+            extend = open_ if rng.random() < 0.4 else (int(rng.integers(-6, 1)) if rng.random() < 0.85 else int(rng.integers(-3, 4)))
+            local = family == 2
+            engine_type = szb.SmithWatermanScores if local else szb.NeedlemanWunschScores
+            got = engine_type(byte_to_class, costs, open=open_, extend=extend)(queries, candidates, device=scope)
+            want = support.oracle_weighted(queries, candidates, byte_to_class, costs, open_, extend, local)
+            label = ("smith_waterman" if local else "needleman_wunsch", open_, extend)
+        assert np.array_equal(got, want), (label, top, len(alphabet), symmetric)
+
+
+def test_c_program_against_the_reference_header(scope):
+    """oracle/_ref/dropin_probe was compiled (in the build container) against the reference's own stringzillas.h and
+    linked against libstringzillas_b200.so; here it must compute d("kitten", "sitting") = 3 on the GPU."""
+    import subprocess
+
+    binary = support.ROOT / "oracle" / "_ref" / "dropin_probe"
+    if not binary.exists():
+        pytest.skip("drop-in probe was not built (no reference tree at build time)")
+    ran = subprocess.run([str(binary)], capture_output=True, text=True)
+    assert ran.returncode == 0 and "status 0 distance 3" in ran.stdout, ran.stdout + ran.stderr
+
+
 def test_row_shards_reassemble_the_matrix(scope):
     rng = np.random.default_rng(23)
     queries = support.random_strings(rng, 13, 0, 200, support.DNA)
