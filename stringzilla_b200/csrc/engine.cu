@@ -163,8 +163,10 @@ struct DeviceBuffer {
     DeviceBuffer() = default;
     DeviceBuffer(DeviceBuffer const &) = delete;
     DeviceBuffer &operator=(DeviceBuffer const &) = delete;
-    ~DeviceBuffer() {
+    ~DeviceBuffer() { release(); }
+    void release() {
         if (ptr) cudaFree(ptr);
+        ptr = nullptr, capacity = 0;
     }
     cudaError_t reserve(size_t bytes) {
         if (bytes <= capacity) return cudaSuccess;
@@ -182,8 +184,10 @@ struct DeviceBuffer {
 struct PinnedBuffer {
     void *ptr = nullptr;
     size_t capacity = 0;
-    ~PinnedBuffer() {
+    ~PinnedBuffer() { release(); }
+    void release() {
         if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr, capacity = 0;
     }
     cudaError_t reserve(size_t bytes) {
         if (bytes <= capacity) return cudaSuccess;
@@ -288,10 +292,15 @@ struct StagedSet {
     std::vector<uint32_t> offsets; // count + 1, relative to the staged blob
     uint32_t longest = 0;
     DeviceBuffer raw, classes, device_offsets;
+    uint8_t const *host_view = nullptr; // the staged bytes as the host can read them (nullptr for device-only input)
     DeviceBuffer rune_counts, rune_offsets, runes; // UTF-8 engines: the decoded symbol streams
     std::vector<uint32_t> rune_counts_host;
     PinnedBuffer gather; // only for callback sequences
     std::vector<uint8_t> offsets_bounce;
+    void release() {
+        raw.release(), classes.release(), device_offsets.release(), rune_counts.release(), rune_offsets.release();
+        runes.release(), gather.release();
+    }
 };
 
 #pragma endregion
@@ -346,6 +355,7 @@ static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, sz
     set.longest = 0;
     uint8_t const *blob = nullptr;
     bool contiguous = true;
+    set.host_view = nullptr;
 
     if (view.layout == InputView::kTape32 || view.layout == InputView::kTape64) {
         void const *offsets_pointer;
@@ -415,7 +425,7 @@ static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, sz
     if (set.total_bytes) {
         if (contiguous) {
             SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, blob, set.total_bytes, cudaMemcpyDefault, stream));
-            if (pointer_is_host_readable(blob)) stats.h2d_bytes += set.total_bytes;
+            if (pointer_is_host_readable(blob)) stats.h2d_bytes += set.total_bytes, set.host_view = blob;
         }
         else {
             auto const *sequence = static_cast<sz_sequence_t const *>(view.object);
@@ -431,6 +441,7 @@ static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, sz
                 SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, set.gather.ptr, set.total_bytes, cudaMemcpyHostToDevice,
                                          stream));
                 stats.h2d_bytes += set.total_bytes;
+                set.host_view = (uint8_t const *)set.gather.ptr;
             }
             else {
                 for (size_t i = 0; i < count; ++i) {
@@ -573,6 +584,17 @@ struct LaunchPlan {
 
 static Failure ensure_events(Engine &engine, int device) {
     if (engine.events_device == device && engine.events[0]) return ok();
+    if (engine.events_device >= 0 && engine.events_device != device) {
+        // The engine moves to another GPU (a scope of a different device): its grow-only buffers live on the old one.
+        cudaSetDevice(engine.events_device);
+        engine.queries.release(), engine.candidates.release();
+        for (DeviceBuffer *buffer : {&engine.results, &engine.scoring, &engine.lut, &engine.flags, &engine.query_flags,
+                                     &engine.slots, &engine.jobs, &engine.order, &engine.counters, &engine.scratch,
+                                     &engine.myers_candidates, &engine.positions})
+            buffer->release();
+        engine.upload.release(), engine.upload_model.release();
+        cudaSetDevice(device);
+    }
     for (cudaEvent_t &event : engine.events) {
         if (event) cudaEventDestroy(event), event = nullptr;
         SZB_CUDA(cudaEventCreate(&event));
@@ -636,29 +658,41 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     uint32_t present[256] = {0};
     bool wide_symbols = false;
     if (engine.algorithm == Algorithm::kLevenshtein) {
-        SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
-        SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
-        if (cs.total_bytes) {
-            byte_presence_kernel<<<296, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
-                                                          engine.flags.as<uint32_t>());
-            SZB_CUDA(cudaGetLastError());
-            stats.kernel_launches++;
-        }
         uint32_t query_present[256] = {0};
-        if (engine.utf8 && !symmetric && qs.total_bytes) {
-            SZB_CUDA(engine.query_flags.reserve(256 * sizeof(uint32_t)));
-            SZB_CUDA(cudaMemsetAsync(engine.query_flags.ptr, 0, 256 * sizeof(uint32_t), stream));
-            byte_presence_kernel<<<296, 512, 0, stream>>>(qs.raw.as<uint8_t>(), qs.total_bytes,
-                                                          engine.query_flags.as<uint32_t>());
-            SZB_CUDA(cudaGetLastError());
-            stats.kernel_launches++;
-            SZB_CUDA(cudaMemcpyAsync(query_present, engine.query_flags.ptr, sizeof(query_present),
-                                     cudaMemcpyDeviceToHost, stream));
-            stats.d2h_bytes += sizeof(query_present);
+        bool const need_queries = engine.utf8 && !symmetric && qs.total_bytes;
+        // Small host-resident inputs are scanned on the host: a kernel plus a D2H round-trip costs more than the scan.
+        constexpr uint64_t host_scan_limit = 512 * 1024;
+        bool const scan_on_host = cs.total_bytes <= host_scan_limit && (cs.host_view || !cs.total_bytes) &&
+                                  (!need_queries || (qs.total_bytes <= host_scan_limit && qs.host_view));
+        if (scan_on_host) {
+            for (uint64_t i = 0; i < cs.total_bytes; ++i) present[cs.host_view[i]] = 1;
+            if (need_queries)
+                for (uint64_t i = 0; i < qs.total_bytes; ++i) query_present[qs.host_view[i]] = 1;
         }
-        SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
-        SZB_CUDA(cudaStreamSynchronize(stream));
-        stats.d2h_bytes += sizeof(present);
+        else {
+            SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
+            SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
+            if (cs.total_bytes) {
+                byte_presence_kernel<<<296, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
+                                                              engine.flags.as<uint32_t>());
+                SZB_CUDA(cudaGetLastError());
+                stats.kernel_launches++;
+            }
+            if (need_queries) {
+                SZB_CUDA(engine.query_flags.reserve(256 * sizeof(uint32_t)));
+                SZB_CUDA(cudaMemsetAsync(engine.query_flags.ptr, 0, 256 * sizeof(uint32_t), stream));
+                byte_presence_kernel<<<296, 512, 0, stream>>>(qs.raw.as<uint8_t>(), qs.total_bytes,
+                                                              engine.query_flags.as<uint32_t>());
+                SZB_CUDA(cudaGetLastError());
+                stats.kernel_launches++;
+                SZB_CUDA(cudaMemcpyAsync(query_present, engine.query_flags.ptr, sizeof(query_present),
+                                         cudaMemcpyDeviceToHost, stream));
+                stats.d2h_bytes += sizeof(query_present);
+            }
+            SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
+            SZB_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += sizeof(present);
+        }
         if (engine.utf8)
             for (int b = 128; b < 256; ++b) wide_symbols |= present[b] != 0 || query_present[b] != 0;
     }
@@ -819,6 +853,35 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         by_length.swap(kept);
     }
     size_t const n_dp_candidates = by_length.size();
+    // A launch that cannot fill the GPU for ~50 us is folded into the next wider one: padding a few candidates to
+    // more words per lane costs less than a dependent launch of its own.
+    if (myers_launches.size() > 1) {
+        uint64_t query_bytes = 0;
+        for (uint32_t q : order) query_bytes += query_length(q);
+        std::sort(myers_launches.begin(), myers_launches.end(),
+                  [](MyersLaunch const &a, MyersLaunch const &b) { return a.words < b.words; });
+        for (size_t l = 0; l + 1 < myers_launches.size();) {
+            uint64_t cells = 0;
+            for (MyersCandidate const &member : myers_launches[l].members)
+                cells += (uint64_t)candidate_length(member.candidate) * query_bytes;
+            if (cells >= 1500000000ull) {
+                ++l;
+                continue;
+            }
+            MyersLaunch &wider = myers_launches[l + 1];
+            for (MyersCandidate member : myers_launches[l].members) {
+                uint32_t lanes = 1;
+                while (32u * wider.words * lanes < candidate_length(member.candidate)) lanes *= 2;
+                member.lanes = lanes;
+                wider.members.push_back(member);
+            }
+            myers_launches.erase(myers_launches.begin() + l);
+        }
+        for (MyersLaunch &launch : myers_launches)
+            std::stable_sort(launch.members.begin(), launch.members.end(), [&](MyersCandidate const &a, MyersCandidate const &b) {
+                return candidate_length(a.candidate) > candidate_length(b.candidate);
+            });
+    }
     // Heaviest launch first, so that the lighter ones fill the tail of the heavier ones.
     auto launch_weight = [&](MyersLaunch const &launch) {
         uint64_t weight = 0;
@@ -929,10 +992,27 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     SZB_CUDA(engine.slots.reserve(slots_bytes));
     SZB_CUDA(engine.jobs.reserve(jobs_bytes));
     SZB_CUDA(engine.counters.reserve((plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64));
-    SZB_CUDA(engine.upload.reserve(order_bytes + slots_bytes + jobs_bytes));
+    std::vector<MyersCandidate> myers_flat; // the bit-parallel launches' candidate lists, back to back
+    for (MyersLaunch const &launch : myers_launches) myers_flat.insert(myers_flat.end(), launch.members.begin(), launch.members.end());
+    size_t const myers_bytes = myers_flat.size() * sizeof(MyersCandidate), position_bytes = position.size() * sizeof(uint32_t);
+    SZB_CUDA(engine.myers_candidates.reserve(myers_bytes));
+    SZB_CUDA(engine.positions.reserve(position_bytes));
+    SZB_CUDA(engine.upload.reserve(order_bytes + slots_bytes + jobs_bytes + myers_bytes + position_bytes));
     {
+        // One pinned arena per engine: nothing here needs a host synchronisation (the call's final sync covers it).
         char *arena = (char *)engine.upload.ptr;
         size_t cursor = 0;
+        if (myers_bytes) {
+            std::memcpy(arena + cursor, myers_flat.data(), myers_bytes);
+            SZB_CUDA(cudaMemcpyAsync(engine.myers_candidates.ptr, arena + cursor, myers_bytes, cudaMemcpyHostToDevice, stream));
+            cursor += myers_bytes;
+        }
+        if (position_bytes) {
+            std::memcpy(arena + cursor, position.data(), position_bytes);
+            SZB_CUDA(cudaMemcpyAsync(engine.positions.ptr, arena + cursor, position_bytes, cudaMemcpyHostToDevice, stream));
+            cursor += position_bytes;
+        }
+        stats.h2d_bytes += myers_bytes + position_bytes;
         std::memcpy(arena + cursor, order.data(), order_bytes);
         SZB_CUDA(cudaMemcpyAsync(engine.order.ptr, arena + cursor, order_bytes, cudaMemcpyHostToDevice, stream));
         cursor += order_bytes;
@@ -950,25 +1030,6 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     // Launches overlap on side streams: every plan gets its own per-CTA boundary scratch.
     if (scratch_words_per_cta)
         SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms * plans.size()));
-
-    // 7a. The bit-parallel launches' candidate lists.
-    std::vector<MyersCandidate> myers_flat;
-    for (MyersLaunch const &launch : myers_launches) myers_flat.insert(myers_flat.end(), launch.members.begin(), launch.members.end());
-    if (!myers_flat.empty()) {
-        SZB_CUDA(engine.myers_candidates.reserve(myers_flat.size() * sizeof(MyersCandidate)));
-        SZB_CUDA(cudaMemcpyAsync(engine.myers_candidates.ptr, myers_flat.data(), myers_flat.size() * sizeof(MyersCandidate),
-                                 cudaMemcpyHostToDevice, stream));
-        SZB_CUDA(cudaStreamSynchronize(stream)); // `myers_flat` is pageable and local
-        stats.h2d_bytes += myers_flat.size() * sizeof(MyersCandidate);
-    }
-
-    if (triangle) {
-        SZB_CUDA(engine.positions.reserve(position.size() * sizeof(uint32_t)));
-        SZB_CUDA(cudaMemcpyAsync(engine.positions.ptr, position.data(), position.size() * sizeof(uint32_t),
-                                 cudaMemcpyHostToDevice, stream));
-        SZB_CUDA(cudaStreamSynchronize(stream)); // `position` is pageable and local
-        stats.h2d_bytes += position.size() * sizeof(uint32_t);
-    }
 
     // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
     SZB_CUDA(cudaEventRecord(engine.events[1], stream));

@@ -372,6 +372,22 @@ def test_row_shards_reassemble_the_matrix(scope):
     assert np.array_equal(out, support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3))
 
 
+def test_engine_follows_the_scope_across_devices():
+    """One engine, scopes on two GPUs (legal per the reference's threading contract, types.cuh:433-444): the engine's
+    grow-only buffers must move with the scope."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(43)
+    queries = support.random_strings(rng, 9, 0, 300, support.DNA)
+    candidates = support.random_strings(rng, 8, 0, 300, support.DNA)
+    want = support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3)
+    engine = szb.LevenshteinDistances(1, 3, 3, 3)
+    for device in (0, 1, 0):
+        assert np.array_equal(engine(queries, candidates, device=szb.DeviceScope(gpu_device=device)), want)
+
+
 def test_full_size_tile_properties_and_sampled_parity(scope):
     """BASELINE config 2 scale (q316 x c317, |s| ~ 1024): size-independent properties over the whole matrix plus
     exact parity on sampled rows (the oracle would need minutes for all 1e11 cells)."""
