@@ -124,7 +124,7 @@ class ClockSampler:
         try:
             self.process = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except OSError:
@@ -203,6 +203,22 @@ def time_reference(family, kwargs, queries, candidates, steps, warmup, budget_se
 # ---------------------------------------------------------------------------------------------------------------------
 # Our arm
 # ---------------------------------------------------------------------------------------------------------------------
+
+
+def ncu_dram_traffic(summary_name: str, kernel_substring: str):
+    """DRAM bytes (read + write) per launch of a kernel, from the committed `ncu --set full` summary under profiles/
+    (tools/ncu_summary.py output); None when the summary is absent. Sums the launches that make up one step."""
+    path = ROOT / "profiles" / summary_name
+    if not path.exists():
+        return None
+    total, inside, scale = 0.0, False, {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for line in path.read_text().splitlines():
+        if line.startswith("## "):
+            inside = kernel_substring in line
+        elif inside and (line.startswith("dram__bytes_read.sum ") or line.startswith("dram__bytes_write.sum ")):
+            parts = line.split()
+            total += float(parts[1]) * scale.get(parts[2], 1)
+    return int(total) if total else None
 
 
 def dpx_peak_lane_ops_per_second():
@@ -378,7 +394,9 @@ def run_ours(args):
                       "smith_waterman": 4.5 if affine else 2.5}[family]
             peak = lane_ops * 2 / k_reference / 1e9 * world
             return {"bound": "dpx-int16-issue", "achieved": round(gcups, 1), "peak": round(peak, 1), "unit": "GCUPS",
-                    "frac": round(gcups / peak, 4), "traffic": None, "kernel": "szb::wavefront_kernel",
+                    "frac": round(gcups / peak, 4),
+                    "traffic": ncu_dram_traffic("r1_v2_wavefront_c2_weird.txt", "wavefront_kernel") if args.workload in ("c2", "c2_weird") else None,
+                    "kernel": "szb::wavefront_kernel",
                     "dpx_instr_per_cell_pair": {"reference_formulation": k_reference, "this_kernel": k_ours},
                     "dpx_pipe_frac": round(gcups * 1e9 / 2 * k_ours / lane_ops / world, 4),
                     "lane_ops_per_s_measured": lane_ops, "hbm": hbm_block(seconds),
@@ -389,7 +407,10 @@ def run_ours(args):
             # Bit-parallel kernel: 7 LOP3 + 2 SHF + 1 IADD3.X per 32-bit word = 10 ALU lane-ops per 32 DP cells.
             peak = lane_ops * 32 / 10 / 1e9 * world
             roofline = {"bound": "alu-issue (bit-parallel, 10 lane-ops per 32 cells)", "achieved": round(kernel_gcups, 1),
-                        "peak": round(peak, 1), "unit": "GCUPS", "frac": round(kernel_gcups / peak, 4), "traffic": None,
+                        "peak": round(peak, 1), "unit": "GCUPS", "frac": round(kernel_gcups / peak, 4),
+                        "traffic": ncu_dram_traffic("r1_v2_myers_c2.txt", "myers_kernel") if args.workload == "c2" else None,
+                        "traffic_note": "DRAM read+write bytes per step from profiles/r1_v2_myers_c2.txt (ncu --set full); "
+                                        f"algorithmic bytes per step: {algorithmic_bytes}",
                         "kernel": "szb::myers_kernel", "lane_ops_per_s_measured": lane_ops,
                         "hbm": hbm_block(kernel_seconds),
                         "kernel_ms_per_launch": round(kernel_seconds * 1e3 / args.steps, 4)}
@@ -458,7 +479,7 @@ def run_reference(args):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=50)
+    parser.add_argument("--steps", type=int, default=200)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", choices=["ours", "reference"], default="ours")
     parser.add_argument("--workload", default="c2")
