@@ -94,6 +94,18 @@ def make_workload(name: str, scale: int = 1):
         gaps = dict(open=-4, extend=-4) if name == "c3_linear" else dict(open=-4, extend=-1)
         label = f"{name}: q{rows * scale} x c{cols} protein, {family} BLOSUM62 gaps {tuple(gaps.values())}"
         return label, family, dict(byte_to_class=byte_to_class, class_substitution_costs=table, **gaps), queries, candidates
+    if name in ("s100_lev", "s100_nw", "s100_sw"):
+        # The reference's other published table: ~100-byte strings, all-pairs tile (similarities/README.md:14-24).
+        rows = cols = 2048
+        alphabet = DNA if name == "s100_lev" else PROTEIN
+        queries = random_strings(rng, rows * scale, 90, 110, alphabet)
+        candidates = random_strings(rng, cols, 90, 110, alphabet)
+        if name == "s100_lev":
+            return f"{name}: q{rows * scale} x c{cols} DNA, len U[90,110], unit-cost Levenshtein", "levenshtein", dict(match=0, mismatch=1, open=1, extend=1), queries, candidates
+        byte_to_class, table = scoring.blosum62()
+        family = "needleman_wunsch" if name == "s100_nw" else "smith_waterman"
+        return (f"{name}: q{rows * scale} x c{cols} protein, len U[90,110], {family} BLOSUM62 gap -4", family,
+                dict(byte_to_class=byte_to_class, class_substitution_costs=table, open=-4, extend=-4), queries, candidates)
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -374,7 +386,7 @@ def run_ours(args):
         # Rooflines. Neither kernel is HBM-bound (~1e-5 algorithmic bytes per cell update): the bound is instruction
         # issue on the integer (ALU) pipe, whose rate — identical for DPX *.16x2, LOP3, SHF and IADD3 on this part —
         # is measured live by tools/microbench/pipe_rates --dpx-peak.
-        lane_ops = dpx_peak_lane_ops_per_second() if world == 1 else None
+        lane_ops = dpx_peak_lane_ops_per_second()  # measured on rank 0's GPU; the peaks below scale it by the GPU count
         affine = kwargs.get("open") != kwargs.get("extend")
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         hbm_peak = json.loads(peaks_file.read_text())["hbm_gbs"] if peaks_file.exists() else 6650.0

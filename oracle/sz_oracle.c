@@ -186,16 +186,16 @@ ORACLE_API int oracle_levenshtein_cross(uint8_t const *q_data, uint64_t const *q
 #pragma omp parallel
     {
         uint64_t *scratch = (uint64_t *)malloc(sizeof(uint64_t) * 6 * (longest + 1));
-#pragma omp for schedule(dynamic, 1)
+#pragma omp for collapse(2) schedule(dynamic, 1)
         for (long long i = 0; i < (long long)q_count; ++i) {
-            size_t const end = symmetric ? (size_t)i + 1 : c_count;
-            for (size_t j = 0; j < end; ++j) {
+            for (long long j = 0; j < (long long)c_count; ++j) {
+                if (symmetric && j > i) continue; /* lower triangle incl. the diagonal, mirrored */
                 uint8_t const *a = q_data + q_off[i], *b = c_data + c_off[j];
                 size_t la = q_off[i + 1] - q_off[i], lb = c_off[j + 1] - c_off[j];
                 uint64_t r = open == extend ? levenshtein_linear(a, la, b, lb, match, mismatch, open, scratch)
                                             : levenshtein_affine(a, la, b, lb, match, mismatch, open, extend, scratch);
-                results[(size_t)i * row_stride + j] = r;
-                if (symmetric && j != (size_t)i) results[j * row_stride + (size_t)i] = r;
+                results[(size_t)i * row_stride + (size_t)j] = r;
+                if (symmetric && j != i) results[(size_t)j * row_stride + (size_t)i] = r;
             }
         }
         free(scratch);
@@ -215,17 +215,17 @@ ORACLE_API int oracle_weighted_cross(uint8_t const *q_data, uint64_t const *q_of
 #pragma omp parallel
     {
         int64_t *scratch = (int64_t *)malloc(sizeof(int64_t) * 6 * (longest + 1));
-#pragma omp for schedule(dynamic, 1)
+#pragma omp for collapse(2) schedule(dynamic, 1)
         for (long long i = 0; i < (long long)q_count; ++i) {
-            size_t const end = symmetric ? (size_t)i + 1 : c_count;
-            for (size_t j = 0; j < end; ++j) {
+            for (long long j = 0; j < (long long)c_count; ++j) {
+                if (symmetric && j > i) continue;
                 uint8_t const *a = q_data + q_off[i], *b = c_data + c_off[j];
                 size_t la = q_off[i + 1] - q_off[i], lb = c_off[j + 1] - c_off[j];
                 int64_t r = open == extend
                                 ? weighted_linear(a, la, b, lb, byte_to_class, costs, open, local, scratch)
                                 : weighted_affine(a, la, b, lb, byte_to_class, costs, open, extend, local, scratch);
-                results[(size_t)i * row_stride + j] = r;
-                if (symmetric && j != (size_t)i) results[j * row_stride + (size_t)i] = r;
+                results[(size_t)i * row_stride + (size_t)j] = r;
+                if (symmetric && j != i) results[(size_t)j * row_stride + (size_t)i] = r;
             }
         }
         free(scratch);

@@ -372,6 +372,28 @@ def test_row_shards_reassemble_the_matrix(scope):
     assert np.array_equal(out, support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3))
 
 
+def test_very_long_and_very_many(scope):
+    """Extremes of the scheduler: strings far beyond one pass of any shape (tens of thousands of characters: many
+    passes, 16-bit -> 32-bit tier switch) and thousands of tiny strings (one job per slot, many empty ones)."""
+    rng = np.random.default_rng(47)
+    long_q = [support.random_strings(rng, 1, n, n, support.DNA)[0] for n in (12000, 40000, 300)]
+    long_c = support.mutated_copies(rng, long_q[:2], 0.05, support.DNA) + [b"ACGT" * 9000]
+    for costs, kwargs in (((0, 1, 1, 1), {}), ((0, 1, 1, 1), {"bit_parallel": False}), ((1, 3, 4, 2), {})):
+        got = szb.LevenshteinDistances(*costs, **kwargs)(long_q, long_c, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(long_q, long_c, *costs)), (costs, kwargs)
+    byte_to_class, table = scoring.blosum62()
+    prot_q = [support.random_strings(rng, 1, n, n, support.PROTEIN)[0] for n in (9000, 150)]
+    prot_c = support.mutated_copies(rng, prot_q[:1], 0.1, support.PROTEIN) + support.random_strings(rng, 1, 5000, 5000, support.PROTEIN)
+    for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+        got = engine_type(byte_to_class, table, open=-4, extend=-1)(prot_q, prot_c, device=scope)
+        assert np.array_equal(got, support.oracle_weighted(prot_q, prot_c, byte_to_class, table, -4, -1, local))
+    tiny_q = support.random_strings(rng, 3000, 0, 9, support.DNA)
+    tiny_c = support.random_strings(rng, 2500, 0, 9, support.DNA)
+    assert np.array_equal(szb.LevenshteinDistances()(tiny_q, tiny_c, device=scope), support.oracle_levenshtein(tiny_q, tiny_c))
+    got = szb.NeedlemanWunschScores(byte_to_class, table, open=-4, extend=-1)(tiny_q[:700], tiny_c[:900], device=scope)
+    assert np.array_equal(got, support.oracle_weighted(tiny_q[:700], tiny_c[:900], byte_to_class, table, -4, -1, False))
+
+
 def test_engine_follows_the_scope_across_devices():
     """One engine, scopes on two GPUs (legal per the reference's threading contract, types.cuh:433-444): the engine's
     grow-only buffers must move with the scope."""

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <string>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #define ITERS 4096
@@ -13,15 +14,15 @@ enum Op {
     OP_VIMAX3_U16X2, OP_VIMAX3_S16X2, OP_VIADDMAX_U16X2, OP_VIADDMAX_S16X2, OP_VIADDMAX_S16X2_RELU, OP_VIMAX_U16X2,
     OP_VIMAX3_S32, OP_VIADDMAX_S32, OP_IADD, OP_IADD3, OP_LOP3, OP_IMAD, OP_PRMT, OP_SHFL, OP_LDS32, OP_LDS128,
     OP_MIX_VIMAX3_IMAD, OP_MIX_VIMAX3_IADD, OP_MIX_VIMAX3_VIADDMAX, OP_MIX_LDS128_4VIMAX3_4IMAD, OP_VIMIN_U16X2_CMP,
-    OP_IMAD_HI, OP_IMAD_WIDE, OP_SHF_FUNNEL, OP_IADD3_CARRY, OP_POPC, OP_COUNT
+    OP_IMAD_HI, OP_IMAD_WIDE, OP_SHF_FUNNEL, OP_IADD3_CARRY, OP_POPC, OP_HMNMX2, OP_MIX_VIADDMAX_HMNMX2, OP_COUNT
 };
 static const char *op_names[] = {
     "vimax3_u16x2", "vimax3_s16x2", "viaddmax_u16x2", "viaddmax_s16x2", "viaddmax_s16x2_relu", "vimax_u16x2",
     "vimax3_s32", "viaddmax_s32", "iadd", "iadd3", "lop3", "imad", "prmt", "shfl_up", "lds32", "lds128",
     "mix_vimax3+imad", "mix_vimax3+iadd", "mix_vimax3+viaddmax", "mix_lds128+4vimax3+4imad", "vimin_u16x2",
-    "imad_hi", "imad_wide", "shf_funnel", "iadd3_carry_chain", "popc", ""};
+    "imad_hi", "imad_wide", "shf_funnel", "iadd3_carry_chain", "popc", "hmnmx2", "mix_viaddmax+hmnmx2", ""};
 // instructions counted per inner iteration per chain
-static const int op_instrs[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 9, 1, 1, 1, 1, 2, 1};
+static const int op_instrs[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 9, 1, 1, 1, 1, 2, 1, 1, 2};
 
 template <int OP>
 __global__ void __launch_bounds__(256) bench(uint32_t *out, uint32_t seed, unsigned long long *cycles) {
@@ -59,6 +60,8 @@ __global__ void __launch_bounds__(256) bench(uint32_t *out, uint32_t seed, unsig
             if (OP == OP_SHF_FUNNEL) x[i] = __funnelshift_l(y[i], x[i], 1);
             if (OP == OP_IADD3_CARRY) { asm("add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3;" : "+r"(x[i]), "+r"(y[i]) : "r"(k), "r"(m)); }
             if (OP == OP_POPC) x[i] = __popc(x[i]) + y[i];
+            if (OP == OP_HMNMX2) { __half2 a = *reinterpret_cast<__half2 *>(&x[i]), b = *reinterpret_cast<__half2 *>(&y[i]); __half2 r = __hmax2(a, b); x[i] = *reinterpret_cast<uint32_t *>(&r) + 1; }
+            if (OP == OP_MIX_VIADDMAX_HMNMX2) { y[i] = __viaddmax_u16x2(y[i], m, k); __half2 a = *reinterpret_cast<__half2 *>(&x[i]), b = *reinterpret_cast<__half2 *>(&y[i]); __half2 r = __hmax2(a, b); x[i] = *reinterpret_cast<uint32_t *>(&r); }
             if (OP == OP_MIX_VIMAX3_IMAD) { y[i] = y[i] * 1 + m; asm volatile("" : "+r"(y[i])); x[i] = __vimax3_u16x2(x[i], y[i], k); }
             if (OP == OP_MIX_VIMAX3_IADD) { y[i] = y[i] + m; x[i] = __vimax3_u16x2(x[i], y[i], k); }
             if (OP == OP_MIX_VIMAX3_VIADDMAX) { y[i] = __viaddmax_u16x2(y[i], m, k); x[i] = __vimax3_u16x2(x[i], y[i], k); }
