@@ -119,6 +119,68 @@ __global__ void utf8_decode_kernel(uint8_t const *bytes, uint32_t const *byte_of
     if (counts) counts[index] = produced;
 }
 
+/**
+ *  Rune compaction for UTF-8 engines. When a call's strings draw on at most 256 distinct runes (any alphabetic script,
+ *  small CJK corpora), ranking them into byte ids turns the rune problem into a byte problem and unlocks every
+ *  byte-level kernel, including the bit-parallel ones. An open-addressing table in global memory collects the runes.
+ */
+constexpr uint32_t kRuneTableSlots = 1u << 16;
+constexpr uint32_t kRuneEmpty = 0xFFFFFFFFu; // no rune: the unchecked decoder yields at most 21 bits
+
+__device__ __forceinline__ uint32_t rune_slot(uint32_t rune) { return (rune * 2654435761u) >> 16; }
+
+__global__ void rune_insert_kernel(uint32_t const *runes, uint64_t n, uint32_t *table, uint32_t *state) {
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t const rune = runes[i];
+        uint32_t slot = rune_slot(rune);
+        for (uint32_t probes = 0;; ++probes, slot = (slot + 1) & (kRuneTableSlots - 1)) {
+            uint32_t const seen = table[slot];
+            if (seen == rune) break;
+            if (seen == kRuneEmpty) {
+                uint32_t const previous = atomicCAS(&table[slot], kRuneEmpty, rune);
+                if (previous == kRuneEmpty || previous == rune) break;
+            }
+            if (probes > 4096) { // hopelessly crowded: far more than 256 distinct runes anyway
+                state[1] = 1;
+                break;
+            }
+        }
+    }
+}
+
+/** One block: ranks the occupied slots in slot order; state[0] = number of distinct runes. */
+__global__ void rune_rank_kernel(uint32_t const *table, uint32_t *ranks, uint32_t *state) {
+    __shared__ uint32_t partial[1024];
+    constexpr uint32_t per_thread = kRuneTableSlots / 1024;
+    uint32_t const first = threadIdx.x * per_thread;
+    uint32_t mine = 0;
+    for (uint32_t i = 0; i < per_thread; ++i) mine += table[first + i] != kRuneEmpty;
+    partial[threadIdx.x] = mine;
+    __syncthreads();
+    for (uint32_t offset = 1; offset < 1024; offset <<= 1) { // Hillis-Steele inclusive scan
+        uint32_t const add = threadIdx.x >= offset ? partial[threadIdx.x - offset] : 0;
+        __syncthreads();
+        partial[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t running = partial[threadIdx.x] - mine;
+    for (uint32_t i = 0; i < per_thread; ++i)
+        if (table[first + i] != kRuneEmpty) ranks[first + i] = running++;
+    if (threadIdx.x == 1023) state[0] = partial[1023];
+}
+
+__global__ void rune_map_kernel(uint32_t const *runes, uint64_t n, uint32_t const *table, uint32_t const *ranks,
+                                uint8_t *out) {
+    uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t const rune = runes[i];
+        uint32_t slot = rune_slot(rune);
+        while (table[slot] != rune) slot = (slot + 1) & (kRuneTableSlots - 1);
+        out[i] = (uint8_t)ranks[slot];
+    }
+}
+
 #pragma endregion
 
 #pragma region Errors
@@ -320,7 +382,7 @@ struct Engine {
 
     // Grow-only device state, one set per engine: engines are not re-entrant.
     StagedSet queries, candidates;
-    DeviceBuffer results, scoring, lut, flags, query_flags, slots, jobs, order, counters, scratch, myers_candidates, positions;
+    DeviceBuffer results, scoring, lut, flags, query_flags, rune_table, rune_ranks, rune_state, slots, jobs, order, counters, scratch, myers_candidates, positions;
     PinnedBuffer upload, upload_model;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     // Independent launches of one call (different strip widths, word counts, families) overlap their tails on side
@@ -589,7 +651,7 @@ static Failure ensure_events(Engine &engine, int device) {
         cudaSetDevice(engine.events_device);
         engine.queries.release(), engine.candidates.release();
         for (DeviceBuffer *buffer : {&engine.results, &engine.scoring, &engine.lut, &engine.flags, &engine.query_flags,
-                                     &engine.slots, &engine.jobs, &engine.order, &engine.counters, &engine.scratch,
+                                     &engine.rune_table, &engine.rune_ranks, &engine.rune_state, &engine.slots, &engine.jobs, &engine.order, &engine.counters, &engine.scratch,
                                      &engine.myers_candidates, &engine.positions})
             buffer->release();
         engine.upload.release(), engine.upload_model.release();
@@ -742,6 +804,70 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         if (Failure failure = decode_set(qs)) return failure;
         if (!symmetric)
             if (Failure failure = decode_set(cs)) return failure;
+
+        // 2b. At most 256 distinct runes in the whole call? Then rank them into byte ids: the rune problem becomes a
+        //     byte problem over a private alphabet, and every byte-level kernel applies (bit-parallel ones included).
+        SZB_CUDA(engine.rune_table.reserve(kRuneTableSlots * sizeof(uint32_t)));
+        SZB_CUDA(engine.rune_ranks.reserve(kRuneTableSlots * sizeof(uint32_t)));
+        SZB_CUDA(engine.rune_state.reserve(2 * sizeof(uint32_t)));
+        SZB_CUDA(cudaMemsetAsync(engine.rune_table.ptr, 0xFF, kRuneTableSlots * sizeof(uint32_t), stream));
+        SZB_CUDA(cudaMemsetAsync(engine.rune_state.ptr, 0, 2 * sizeof(uint32_t), stream));
+        auto for_each_side = [&](auto &&apply) -> Failure {
+            if (Failure failure = apply(qs)) return failure;
+            if (!symmetric)
+                if (Failure failure = apply(cs)) return failure;
+            return ok();
+        };
+        auto grid_for = [](uint64_t n) { return (int)std::min<uint64_t>((n + 255) / 256, 148 * 8); };
+        if (Failure failure = for_each_side([&](StagedSet &set) -> Failure {
+                uint64_t const n = set.offsets[set.count];
+                if (!n) return ok();
+                rune_insert_kernel<<<grid_for(n), 256, 0, stream>>>(set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(),
+                                                                    engine.rune_state.as<uint32_t>());
+                SZB_CUDA(cudaGetLastError());
+                stats.kernel_launches++;
+                return ok();
+            }))
+            return failure;
+        rune_rank_kernel<<<1, 1024, 0, stream>>>(engine.rune_table.as<uint32_t>(), engine.rune_ranks.as<uint32_t>(),
+                                                 engine.rune_state.as<uint32_t>());
+        SZB_CUDA(cudaGetLastError());
+        stats.kernel_launches++;
+        uint32_t rune_state[2] = {0, 0};
+        SZB_CUDA(cudaMemcpyAsync(rune_state, engine.rune_state.ptr, sizeof(rune_state), cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += sizeof(rune_state);
+        if (rune_state[1] == 0 && rune_state[0] <= 256) {
+            if (Failure failure = for_each_side([&](StagedSet &set) -> Failure {
+                    uint64_t const n = set.offsets[set.count];
+                    // The id stream overwrites the staged UTF-8 bytes (never longer than them) and the symbol offsets
+                    // become the byte offsets of the byte-level problem.
+                    if (n) {
+                        rune_map_kernel<<<grid_for(n), 256, 0, stream>>>(set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(),
+                                                                         engine.rune_ranks.as<uint32_t>(), set.raw.as<uint8_t>());
+                        SZB_CUDA(cudaGetLastError());
+                        stats.kernel_launches++;
+                    }
+                    SZB_CUDA(cudaMemcpyAsync(set.device_offsets.ptr, set.rune_offsets.ptr, (set.count + 1) * sizeof(uint32_t),
+                                             cudaMemcpyDeviceToDevice, stream));
+                    set.total_bytes = n;
+                    set.host_view = nullptr;
+                    return ok();
+                }))
+                return failure;
+            wide_symbols = false;
+            std::memset(present, 0, sizeof(present));
+            SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
+            SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
+            if (cs.total_bytes) {
+                byte_presence_kernel<<<296, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes, engine.flags.as<uint32_t>());
+                SZB_CUDA(cudaGetLastError());
+                stats.kernel_launches++;
+            }
+            SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
+            SZB_CUDA(cudaStreamSynchronize(stream));
+            stats.d2h_bytes += sizeof(present);
+        }
     }
     Model model;
     build_model(engine, present, wide_symbols, model);

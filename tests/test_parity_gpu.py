@@ -262,6 +262,18 @@ def test_utf8_levenshtein_rune_level(scope):
         assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, candidates, *costs)), costs
     got = szb.LevenshteinDistancesUTF8()(queries, device=scope)
     assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, None))
+    # More than 256 distinct runes in one call: no byte ranking exists, the 32-bit symbol recurrences take over.
+    cjk = [chr(0x4E00 + i) for i in range(2000)]
+    wide_text = lambda n: "".join(cjk[i] for i in rng.integers(0, len(cjk), size=n)).encode()
+    wide_q = [wide_text(int(n)) for n in rng.integers(0, 500, size=7)] + [text(40)]
+    wide_c = [wide_text(int(n)) for n in rng.integers(0, 700, size=6)] + [wide_q[0][: 3 * 50], b"ascii too"]
+    for costs in ((0, 1, 1, 1), (0, 4, 3, 2)):
+        engine = szb.LevenshteinDistancesUTF8(*costs)
+        assert np.array_equal(engine(wide_q, wide_c, device=scope), support.oracle_levenshtein_utf8(wide_q, wide_c, *costs))
+        assert engine.last_call_stats.pairs_s32 > 0
+    few = szb.LevenshteinDistancesUTF8()
+    assert np.array_equal(few(queries, candidates, device=scope), support.oracle_levenshtein_utf8(queries, candidates))
+    assert few.last_call_stats.pairs_bit_parallel > 0  # ~40 distinct runes: ranked into bytes, bit-parallel kernel
     ascii_q = support.random_strings(rng, 8, 0, 300, b"abcdefghij ")
     ascii_c = support.random_strings(rng, 7, 0, 300, b"abcdefghij ")
     rune_level = szb.LevenshteinDistancesUTF8()
