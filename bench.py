@@ -61,17 +61,17 @@ def make_workload(name: str, scale: int = 1):
     from stringzilla_b200 import scoring
 
     rng = np.random.default_rng(42)
-    if name in ("c2", "c2_weird", "c1", "c2_text"):
+    if name in ("c2", "c2_weird", "c1", "c2_text", "c2_text_weird"):
         if name == "c1":
             rows, cols, low, high = 32, 32, 64, 256
         else:
             rows, cols, low, high = 316, 317, 960, 1088
         # "c2_text": the same tile over a 64-symbol alphabet, the regime of natural-language bytes (> 31 classes).
-        alphabet = DNA if name != "c2_text" else bytes(range(48, 112))
+        alphabet = DNA if not name.startswith("c2_text") else bytes(range(48, 112))
         queries = random_strings(rng, rows * scale, low, high, alphabet)
         candidates = random_strings(rng, cols, low, high, alphabet)
-        costs = dict(match=0, mismatch=1, open=1, extend=1) if name != "c2_weird" else dict(match=1, mismatch=3, open=3, extend=3)
-        kind = "DNA" if name != "c2_text" else "64-symbol text"
+        costs = dict(match=0, mismatch=1, open=1, extend=1) if "weird" not in name else dict(match=1, mismatch=3, open=3, extend=3)
+        kind = "DNA" if not name.startswith("c2_text") else "64-symbol text"
         label = f"{name}: q{rows * scale} x c{cols} {kind}, len U[{low},{high}], Levenshtein costs {tuple(costs.values())}"
         return label, "levenshtein", costs, queries, candidates
     if name in ("c3", "c3_linear", "c3_sw", "c4", "c5"):

@@ -586,7 +586,15 @@ static void build_model(Engine const &engine, uint32_t const *present, bool wide
     model.family32 = local ? (linear ? FAM_S32_LOCAL_LIN : FAM_S32_LOCAL_AFF)
                            : (linear ? FAM_S32_GLOBAL_LIN : FAM_S32_GLOBAL_AFF);
     model.family16 = -1;
-    if (sc.compare) return; // large alphabets: byte-compare recurrences exist only in the 32-bit tier for now
+    if (sc.compare) {
+        // Large raw-byte alphabets: the packed tier has a byte-compare flavour of the shifted linear recurrence only;
+        // it needs a match to score at least as well as a mismatch (the XOR trick subtracts a non-negative drop).
+        if (!wide_symbols && linear && sc.match >= sc.mismatch) {
+            model.family16 = FAM_LIN_COMPARE;
+            model.range_offset = 0, model.range_per_step = std::max(smax - 2 * sc.open, 0);
+        }
+        return;
+    }
 
     int const open = sc.open, extend = sc.extend;
     if (!local && linear) {
@@ -1030,6 +1038,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     // Register budget (128 per thread) caps the strip width per family: packed affine recurrences keep two strips per
     // lane (36 columns), the 32-bit tier adds the strip's symbols for compare mode (32 linear / 20 affine).
     auto widest_strip = [](int family) {
+        if (family == FAM_LIN_COMPARE) return 32; // strip cells + strip bytes
         if (family >= FAM_S32_GLOBAL_LIN) return family_is_affine(family) ? 20 : 32;
         return family_is_affine(family) ? 36 : 40;
     };
@@ -1069,7 +1078,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     std::vector<Job> host_jobs;
     std::vector<LaunchPlan> plans;
     uint64_t scratch_words_per_cta = 0;
-    for (int family = 0; family < 8; ++family) {
+    for (int family = 0; family < kFamilyCount; ++family) {
         for (int strip = kStripCount - 1; strip >= 0; --strip) {
             // Longest slots first: their jobs are the heaviest, and the atomic job counter hands them out in order.
             std::vector<uint32_t> members;
@@ -1293,7 +1302,8 @@ cudaError_t launch_wavefront(int family, int shape, int grid, size_t smem, cudaS
     case FAM_S32_GLOBAL_LIN: return launch_family<FAM_S32_GLOBAL_LIN>(shape, grid, smem, stream, args);
     case FAM_S32_GLOBAL_AFF: return launch_family<FAM_S32_GLOBAL_AFF>(shape, grid, smem, stream, args);
     case FAM_S32_LOCAL_LIN: return launch_family<FAM_S32_LOCAL_LIN>(shape, grid, smem, stream, args);
-    default: return launch_family<FAM_S32_LOCAL_AFF>(shape, grid, smem, stream, args);
+    case FAM_S32_LOCAL_AFF: return launch_family<FAM_S32_LOCAL_AFF>(shape, grid, smem, stream, args);
+    default: return launch_family<FAM_LIN_COMPARE>(shape, grid, smem, stream, args);
     }
 }
 

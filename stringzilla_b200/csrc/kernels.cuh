@@ -55,7 +55,9 @@ enum Family : int {
     FAM_S32_GLOBAL_AFF = 5,
     FAM_S32_LOCAL_LIN = 6,
     FAM_S32_LOCAL_AFF = 7,
+    FAM_LIN_COMPARE = 8, ///< FAM_LIN_SHIFT whose substitution term is a packed byte comparison instead of a profile read
 };
+constexpr int kFamilyCount = 9;
 
 constexpr int kThreads = 512;                  ///< 16 warps per persistent CTA, one CTA per SM
 constexpr uint32_t kNoCandidate = 0xFFFFFFFFu; ///< `CandSlot::c1` of an unpaired slot
@@ -109,7 +111,8 @@ __device__ __forceinline__ uint32_t pack_bits(int v) { return ((uint32_t)v & 0xF
 
 template <int FAM>
 struct family_traits {
-    static constexpr bool packed = FAM <= FAM_SW_AFF;
+    static constexpr bool packed = FAM <= FAM_SW_AFF || FAM == FAM_LIN_COMPARE;
+    static constexpr bool linear_shift = FAM == FAM_LIN_SHIFT || FAM == FAM_LIN_COMPARE;
     static constexpr bool affine =
         FAM == FAM_AFF_SHIFT || FAM == FAM_SW_AFF || FAM == FAM_S32_GLOBAL_AFF || FAM == FAM_S32_LOCAL_AFF;
     static constexpr bool local =
@@ -121,7 +124,7 @@ template <int FAM>
 __device__ __forceinline__ int profile_term(int8_t const *sub, int a, int b, bool valid, int open, int extend,
                                             int bias) {
     int const s = valid ? (int)sub[a * 32 + b] : 0;
-    if constexpr (FAM == FAM_LIN_SHIFT) { return valid ? max(s - 2 * open, 0) : 0; }
+    if constexpr (family_traits<FAM>::linear_shift) { return valid ? max(s - 2 * open, 0) : 0; }
     else if constexpr (FAM == FAM_AFF_SHIFT) { return valid ? max(s, 2 * open) - 2 * extend : 2 * (open - extend); }
     else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) { return valid ? s : -bias; }
     else { return valid ? s : -(1 << 28); }
@@ -145,6 +148,8 @@ struct SweepConstants {
     uint32_t gap_bits;     // FAM_SW_*: "+ open" for VIADDMNMX
     uint32_t gap_arith;    // FAM_SW_LIN: "+ g" through a plain add
     uint32_t ext_arith;    // FAM_SW_AFF: "+ extend" through a plain add
+    uint32_t cmp_match_bits; // FAM_LIN_SHIFT compare mode: e(match) in both halves
+    uint32_t cmp_drop_bits;  // FAM_LIN_SHIFT compare mode: e(match) - e(mismatch) >= 0 in both halves
 };
 
 /**
@@ -164,7 +169,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
     int const lane = threadIdx.x & 31;
     int const gl = lane & (G - 1), gi = lane / G;
     int const open = sc.open, extend = sc.extend, bias = sc.bias, go = sc.go;
-    bool const compare = !packed && sc.compare;
+    bool const compare = FAM == FAM_LIN_COMPARE || (!packed && sc.compare);
 
     uint32_t const q_pos = batch * GROUPS + gi;
     bool const q_valid = q_pos < n_queries;
@@ -190,15 +195,28 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
 
     // Top boundary: DP row 0 of the strip, and the seeds of the gap tracks.
     uint32_t h[K], f[affine ? K : 1];
-    uint32_t cb[(!packed) ? K : 1]; // compare mode: the strip's candidate symbols (bytes, or runes when wide)
+    // Compare mode: the strip's candidate symbols — bytes (or runes when wide) in the 32-bit tier; in the packed linear
+    // family both candidates' bytes, pre-shifted so that any mismatch XORs to at least 256: (c0 << 8) | (c1 << 24).
+    uint32_t cb[(!packed || FAM == FAM_LIN_COMPARE) ? K : 1];
     bool const wide = !packed && args.wide_symbols != 0;
     uint32_t const *const q_wide = (uint32_t const *)args.q_cls + q_begin_off;
     uint32_t diag_in, w_out = 0, e_out = 0, best = 0;
     uint32_t left_boundary = 0, left_gap_boundary = 0; // pass 0, lane 0: DP column 0 (packed families: constant)
-    if constexpr (FAM == FAM_LIN_SHIFT) {
+    if constexpr (traits::linear_shift) {
 #pragma unroll
         for (int k = 0; k < K; ++k) h[k] = 0;
         diag_in = 0;
+        if constexpr (FAM == FAM_LIN_COMPARE) {
+            uint8_t const *const c1_ptr = slot.c1 != kNoCandidate ? args.c_cls + args.c_off[slot.c1] : c0_ptr;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                uint32_t const col = (uint32_t)cbase + k;
+                // Padding halves hold 0x00FF: never equal to a shifted byte, and any XOR with one stays >= 255.
+                uint32_t const low = col < slot.len0 ? (uint32_t)c0_ptr[col] << 8 : 0x00FFu;
+                uint32_t const high = col < slot.len1 ? (uint32_t)c1_ptr[col] << 8 : 0x00FFu;
+                cb[k] = low | (high << 16);
+            }
+        }
     }
     else if constexpr (FAM == FAM_AFF_SHIFT) {
         uint32_t const top = pack_bits(bias - go);
@@ -289,6 +307,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         if (valid) {
             uint32_t d = diag_in, l = w_in, e = e_in;
             uint32_t const row_address = strip_address + a * row_bytes;
+            uint32_t const a_twice = a * 0x01000100u; // compare mode of the packed family: the row byte in both halves
 #pragma unroll
             for (int v = 0; v < VECS; ++v) {
                 uint32_t p[4];
@@ -303,6 +322,12 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                         for (int i = 0; i < 4; ++i)
                             p[i] = (uint32_t)(cb[v * 4 + i] == a ? sc.cmp_match : sc.cmp_mismatch);
                     }
+                    else if constexpr (FAM == FAM_LIN_COMPARE) {
+                        // e = e(match) - min(byte XOR, drop): the XOR is 0 on a match and >= 255 >= drop otherwise.
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            p[i] = sc.cmp_match_bits - __vminu2(cb[v * 4 + i] ^ a_twice, sc.cmp_drop_bits);
+                    }
                 }
                 // The four diagonal terms of this vector depend only on the previous row: form them before the
                 // cells of the current row overwrite the strip.
@@ -312,7 +337,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     int const k = v * 4 + i;
-                    if constexpr (FAM == FAM_LIN_SHIFT) { l = h[k] = __vimax3_u16x2(t4[i], h[k], l); }
+                    if constexpr (traits::linear_shift) { l = h[k] = __vimax3_u16x2(t4[i], h[k], l); }
                     else if constexpr (FAM == FAM_AFF_SHIFT) {
                         f[k] = __viaddmax_u16x2(h[k], sc.neg_go_bits, f[k]);
                         e = __viaddmax_u16x2(l, sc.neg_go_bits, e);
@@ -386,7 +411,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                 if (k == k_star) cell = h[k];
             if (gl == lane_star && q_valid) {
                 int64_t score;
-                if constexpr (FAM == FAM_LIN_SHIFT)
+                if constexpr (traits::linear_shift)
                     score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) + (int64_t)(m + n) * open;
                 else if constexpr (FAM == FAM_AFF_SHIFT)
                     score = (int64_t)((cell >> (16 * half)) & 0xFFFFu) - bias + (int64_t)(m + n) * extend;
@@ -435,7 +460,11 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     sc.open = sc_global->open, sc.extend = sc_global->extend, sc.bias = sc_global->bias;
     sc.go = sc.extend - sc.open, sc.negate = sc_global->negate;
     sc.cmp_match = sc_global->match, sc.cmp_mismatch = sc_global->mismatch;
-    sc.compare = !packed && sc_global->compare != 0;
+    sc.compare = FAM == FAM_LIN_COMPARE || (!packed && sc_global->compare != 0);
+    {   // Byte-compare flavour of the shifted linear recurrence: e = max(S - 2g, 0) for the two possible S.
+        int const e_match = max(sc.cmp_match - 2 * sc.open, 0), e_mismatch = max(sc.cmp_mismatch - 2 * sc.open, 0);
+        sc.cmp_match_bits = pack_bits(e_match), sc.cmp_drop_bits = pack_bits(e_match - e_mismatch);
+    }
     sc.neg_go_bits = pack_bits(-sc.go), sc.bias_bits = pack_bits(sc.bias), sc.gap_bits = pack_bits(sc.open);
     sc.gap_arith = pack_arith(sc.open, sc.open), sc.ext_arith = pack_arith(sc.extend, sc.extend);
 

@@ -211,9 +211,13 @@ def test_large_alphabets_and_wide_cells(scope):
     every_byte = bytes(range(256))
     queries = support.random_strings(rng, 9, 0, 700, every_byte)
     candidates = support.mutated_copies(rng, queries, 0.3, every_byte)
-    for costs in ((0, 1, 1, 1), (1, 3, 4, 2)):
-        got = szb.LevenshteinDistances(*costs)(queries, candidates, device=scope)
-        assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs))
+    for costs in ((0, 1, 1, 1), (1, 3, 4, 2), (1, 3, 3, 3), (0, 5, 2, 2), (2, 1, 3, 3)):
+        engine = szb.LevenshteinDistances(*costs, bit_parallel=False)
+        got = engine(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs)), costs
+        # Linear gaps with match <= mismatch take the packed byte-compare recurrence; the rest the 32-bit tier.
+        packed = costs[2] == costs[3] and costs[0] <= costs[1]
+        assert (engine.last_call_stats.pairs_u16 > 0) == packed, costs
     binary_q = support.random_strings(rng, 5, 600, 800, b"ab")
     binary_c = support.random_strings(rng, 6, 600, 800, b"ab")
     for costs in ((0, 100, 100, 100), (0, 127, 90, 60)):
