@@ -18,7 +18,9 @@
 #include "myers.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -685,8 +687,20 @@ static Failure ensure_events(Engine &engine, int device) {
  *  @brief Scores query rows [row_begin, row_end) against every candidate and writes `results[q * stride + c]`.
  *         `candidates.object == nullptr` requests the symmetric self-similarity of the queries.
  */
+/** `SZB200_TRACE=1` prints host-side wall-clock marks of one call to stderr (diagnostics only). */
+struct Trace {
+    bool enabled = std::getenv("SZB200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
+    void mark(char const *what) const {
+        if (!enabled) return;
+        double const us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - start).count();
+        std::fprintf(stderr, "[szb200] %8.1f us  %s\n", us, what);
+    }
+};
+
 static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
                      size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
+    Trace const trace;
     if (scope.kind == Scope::kCpu)
         return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
     if (device_sm_code(scope.gpu_device) == 0 && visible_device_count() <= scope.gpu_device)
@@ -724,6 +738,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     if (n_queries >= 0xFFFFFFF0ull || n_candidates >= 0xFFFFFFF0ull)
         return fail(sz_overflow_risk_k, "Too many strings for one call");
 
+    trace.mark("staged");
     // 2. The scoring model; Levenshtein compacts the alphabet of the candidates into <= 31 classes.
     uint32_t present[256] = {0};
     bool wide_symbols = false;
@@ -877,6 +892,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             stats.d2h_bytes += sizeof(present);
         }
     }
+    trace.mark("alphabet known");
     Model model;
     build_model(engine, present, wide_symbols, model);
     if (!fits_s32(engine, (uint64_t)qs.longest + cs.longest))
@@ -917,12 +933,20 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         q_classes = qs.classes.as<uint8_t>(), c_classes = cs.classes.as<uint8_t>();
     }
 
+    trace.mark("classes mapped (async)");
     // 4. Query order: longest first, so that the batches a warp sweeps together have similar lengths and the heavy
     //    jobs start early.
-    std::vector<uint32_t> order(n_rows);
-    std::iota(order.begin(), order.end(), (uint32_t)row_begin);
     auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return query_length(a) > query_length(b); });
+    std::vector<uint32_t> order(n_rows);
+    {   // One 64-bit key per string — (inverted length, index) — sorts stably with a plain integer sort.
+        std::vector<uint64_t> keys(n_rows);
+        for (size_t i = 0; i < n_rows; ++i) {
+            uint32_t const q = (uint32_t)(row_begin + i);
+            keys[i] = ((uint64_t)(0xFFFFFFFFu - query_length(q)) << 32) | q;
+        }
+        std::sort(keys.begin(), keys.end());
+        for (size_t i = 0; i < n_rows; ++i) order[i] = (uint32_t)keys[i];
+    }
     uint32_t const longest_query = query_length(order[0]);
 
     // Symmetric self-similarity under a symmetric cost model: score every unordered pair once, with the string that
@@ -937,12 +961,16 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     }
     auto rows_needed = [&](uint32_t candidate) { return triangle ? position[candidate] + 1 : (uint32_t)n_rows; };
 
+    trace.mark("queries ordered");
     // 5. Slots: candidates sorted by length; neighbours share a register in the packed tier.
-    std::vector<uint32_t> by_length(n_candidates);
-    std::iota(by_length.begin(), by_length.end(), 0u);
     auto candidate_length = [&](uint32_t c) { return cs.offsets[c + 1] - cs.offsets[c]; };
-    std::stable_sort(by_length.begin(), by_length.end(),
-                     [&](uint32_t a, uint32_t b) { return candidate_length(a) < candidate_length(b); });
+    std::vector<uint32_t> by_length(n_candidates);
+    {
+        std::vector<uint64_t> keys(n_candidates);
+        for (size_t c = 0; c < n_candidates; ++c) keys[c] = ((uint64_t)candidate_length((uint32_t)c) << 32) | (uint32_t)c;
+        std::sort(keys.begin(), keys.end());
+        for (size_t c = 0; c < n_candidates; ++c) by_length[c] = (uint32_t)keys[c];
+    }
 
     // 5a. Unit-cost Levenshtein over a compact alphabet: candidates the bit-parallel kernel covers leave the DP tiers.
     struct MyersLaunch {
@@ -969,18 +997,31 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         // warps per CTA), or the whole carve-out for a CTA-shared one.
         size_t const table_budget = myers_shared_table ? 220 * 1024 - 1024 : 12 * 1024;
         int const max_words = (int)(table_budget / ((size_t)myers_rows * 32 * 4));
+        uint32_t remembered_length = 0xFFFFFFFFu;
+        int remembered_words = 0, remembered_lanes = 0;
+        MyersLaunch *remembered_launch = nullptr;
         for (size_t i = n_candidates; i-- > 0;) { // longest first
             uint32_t const c = by_length[i], length = candidate_length(c);
-            int words = 0, lanes = 0;
-            myers_shape_for_length(length, max_words, words, lanes);
+            // Candidates arrive sorted by length: equal lengths are neighbours, so one remembered answer suffices.
+            if (length != remembered_length) {
+                myers_shape_for_length(length, max_words, remembered_words, remembered_lanes);
+                remembered_length = length;
+            }
+            int const words = remembered_words, lanes = remembered_lanes;
             if (words == 0) {
                 kept.push_back(c);
                 continue;
             }
-            auto launch = std::find_if(myers_launches.begin(), myers_launches.end(),
-                                       [&](MyersLaunch const &l) { return l.words == words; });
-            if (launch == myers_launches.end()) myers_launches.push_back({words, {}}), launch = myers_launches.end() - 1;
-            launch->members.push_back({c, (uint32_t)lanes, rows_needed(c)});
+            if (!remembered_launch || remembered_launch->words != words) {
+                auto launch = std::find_if(myers_launches.begin(), myers_launches.end(),
+                                           [&](MyersLaunch const &l) { return l.words == words; });
+                if (launch == myers_launches.end()) {
+                    myers_launches.reserve(kMyersMaxWords); // keeps `remembered_launch` valid across push_backs
+                    myers_launches.push_back({words, {}}), launch = myers_launches.end() - 1;
+                }
+                remembered_launch = &*launch;
+            }
+            remembered_launch->members.push_back({c, (uint32_t)lanes, rows_needed(c)});
             cells_myers += (uint64_t)length * query_bytes;
         }
         std::reverse(kept.begin(), kept.end()); // back to ascending length for the slot builder
@@ -1073,6 +1114,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
     (void)cells_myers;
 
+    trace.mark("slots built");
     // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
     int const device_sms = std::max(1, device_facts(scope.gpu_device).sms);
     std::vector<Job> host_jobs;
@@ -1118,6 +1160,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         }
     }
 
+    trace.mark("jobs built");
     // 7. Upload the work list.
     std::vector<CandSlot> device_slots(host_slots.size());
     for (size_t s = 0; s < host_slots.size(); ++s) device_slots[s] = host_slots[s].slot;
@@ -1166,6 +1209,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     if (scratch_words_per_cta)
         SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms * plans.size()));
 
+    trace.mark("work list uploaded");
     // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
     SZB_CUDA(cudaEventRecord(engine.events[1], stream));
     size_t const n_launches = myers_launches.size() + plans.size();
@@ -1262,6 +1306,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     }
     SZB_CUDA(cudaEventRecord(engine.events[2], stream));
 
+    trace.mark("kernels launched");
     // 9. Results home: a strided 2-D copy into the caller's matrix (host, pinned, managed or device memory).
     SZB_CUDA(cudaMemcpy2DAsync((int64_t *)results + row_begin * stride, stride * sizeof(int64_t), engine.results.ptr,
                                n_candidates * sizeof(int64_t), n_candidates * sizeof(int64_t), n_rows,
@@ -1270,6 +1315,7 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     SZB_CUDA(cudaEventRecord(engine.events[3], stream));
     SZB_CUDA(cudaStreamSynchronize(stream));
 
+    trace.mark("stream drained");
     float kernel_ms = 0, total_ms = 0;
     cudaEventElapsedTime(&kernel_ms, engine.events[1], engine.events[2]);
     cudaEventElapsedTime(&total_ms, engine.events[0], engine.events[3]);
