@@ -646,7 +646,6 @@ static bool fits_s32(Engine const &engine, uint64_t total_length) {
 
 struct LaunchPlan {
     int family, strip_index;
-    int widest_coverage; // sizes the dynamic shared memory of the launch
     uint32_t first_job, n_jobs;
 };
 
@@ -1112,7 +1111,6 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         i += 1;
     }
     for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
-    (void)cells_myers;
 
     trace.mark("slots built");
     // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
@@ -1127,14 +1125,13 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             for (uint32_t s = (uint32_t)host_slots.size(); s-- > 0;)
                 if (host_slots[s].family == family && host_slots[s].shape.strip_index == strip) members.push_back(s);
             if (members.empty()) continue;
-            LaunchPlan plan = {family, strip, 0, (uint32_t)host_jobs.size(), 0};
+            LaunchPlan plan = {family, strip, (uint32_t)host_jobs.size(), 0};
             bool const affine = family_is_affine(family);
             uint64_t const target_jobs = (uint64_t)device_sms * 8;
             uint64_t const wanted_blocks = (target_jobs + members.size() - 1) / members.size();
             for (uint32_t s : members) {
                 CandSlot const &slot = host_slots[s].slot;
                 Shape const shape = host_slots[s].shape;
-                plan.widest_coverage = std::max(plan.widest_coverage, shape.coverage());
                 // A block is a whole number of rounds of the CTA's warps (each sweeps 32 / G queries at a time),
                 // so that no warp idles at the job's barrier while others run an extra round.
                 uint32_t const round = (uint32_t)(kThreads / 32) * (32 / shape.lanes);
