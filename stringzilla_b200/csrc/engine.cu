@@ -686,61 +686,17 @@ static Failure ensure_events(Engine &engine, int device) {
  *  @brief Scores query rows [row_begin, row_end) against every candidate and writes `results[q * stride + c]`.
  *         `candidates.object == nullptr` requests the symmetric self-similarity of the queries.
  */
-/** `SZB200_TRACE=1` prints host-side wall-clock marks of one call to stderr (diagnostics only). */
-struct Trace {
-    bool enabled = std::getenv("SZB200_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
-    void mark(char const *what) const {
-        if (!enabled) return;
-        double const us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - start).count();
-        std::fprintf(stderr, "[szb200] %8.1f us  %s\n", us, what);
-    }
-};
-
-static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
-                     size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
-    Trace const trace;
-    if (scope.kind == Scope::kCpu)
-        return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
-    if (device_sm_code(scope.gpu_device) == 0 && visible_device_count() <= scope.gpu_device)
-        return fail(sz_missing_gpu_k, "No CUDA device is visible");
-    if (device_sm_code(scope.gpu_device) < 100)
-        return fail(sz_missing_gpu_k, "stringzillas_b200 kernels require an sm_100-class (Blackwell) device");
-    if (Failure failure = scope.ensure_stream()) return failure;
-    cudaStream_t const stream = scope.stream;
-    std::lock_guard<std::mutex> engine_lock(engine.mutex);
-    if (Failure failure = ensure_events(engine, scope.gpu_device)) return failure;
-
-    bool const symmetric = candidates_view.object == nullptr;
-    szs_b200_call_stats_t stats = {};
-    SZB_CUDA(cudaEventRecord(engine.events[0], stream));
-
-    // 1. Stage both sides.
-    if (Failure failure = stage_set(queries_view, engine.queries, stream, stats)) return failure;
-    StagedSet &qs = engine.queries;
-    if (!symmetric)
-        if (Failure failure = stage_set(candidates_view, engine.candidates, stream, stats)) return failure;
-    StagedSet &cs = symmetric ? engine.queries : engine.candidates;
-
-    size_t const n_queries = qs.count, n_candidates = cs.count;
-    if (whole_matrix) row_begin = 0, row_end = n_queries;
-    if (row_end > n_queries || row_begin > row_end) return fail(sz_unexpected_dimensions_k, "Row range out of bounds");
-    if (n_candidates && stride < n_candidates)
-        return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
-    size_t const n_rows = row_end - row_begin;
-    if (n_rows == 0 || n_candidates == 0) {
-        SZB_CUDA(cudaStreamSynchronize(stream));
-        engine.stats = stats;
-        return ok();
-    }
-    if (!results) return fail(sz_unexpected_dimensions_k, "Results pointer is null");
-    if (n_queries >= 0xFFFFFFF0ull || n_candidates >= 0xFFFFFFF0ull)
-        return fail(sz_overflow_risk_k, "Too many strings for one call");
-
-    trace.mark("staged");
+/**
+ *  @brief Steps 2-2b of a call: which symbols are we scoring?
+ *
+ *  Levenshtein engines learn which byte values the candidates contain (`present`), so that the alphabet can be compacted
+ *  into classes. UTF-8 engines additionally decide between three representations: pure ASCII stays bytes; at most 256
+ *  distinct runes are ranked into byte ids (the staged byte streams and offsets are REPLACED by the id streams);
+ *  anything else becomes UTF-32 symbol streams (`wide_symbols`), with offsets and lengths counted in symbols.
+ */
+static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetric, StagedSet &qs, StagedSet &cs,
+                               szs_b200_call_stats_t &stats, uint32_t (&present)[256], bool &wide_symbols) {
     // 2. The scoring model; Levenshtein compacts the alphabet of the candidates into <= 31 classes.
-    uint32_t present[256] = {0};
-    bool wide_symbols = false;
     if (engine.algorithm == Algorithm::kLevenshtein) {
         uint32_t query_present[256] = {0};
         bool const need_queries = engine.utf8 && !symmetric && qs.total_bytes;
@@ -891,6 +847,65 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             stats.d2h_bytes += sizeof(present);
         }
     }
+    return ok();
+}
+
+/** `SZB200_TRACE=1` prints host-side wall-clock marks of one call to stderr (diagnostics only). */
+struct Trace {
+    bool enabled = std::getenv("SZB200_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
+    void mark(char const *what) const {
+        if (!enabled) return;
+        double const us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - start).count();
+        std::fprintf(stderr, "[szb200] %8.1f us  %s\n", us, what);
+    }
+};
+
+static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
+                     size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
+    Trace const trace;
+    if (scope.kind == Scope::kCpu)
+        return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
+    if (device_sm_code(scope.gpu_device) == 0 && visible_device_count() <= scope.gpu_device)
+        return fail(sz_missing_gpu_k, "No CUDA device is visible");
+    if (device_sm_code(scope.gpu_device) < 100)
+        return fail(sz_missing_gpu_k, "stringzillas_b200 kernels require an sm_100-class (Blackwell) device");
+    if (Failure failure = scope.ensure_stream()) return failure;
+    cudaStream_t const stream = scope.stream;
+    std::lock_guard<std::mutex> engine_lock(engine.mutex);
+    if (Failure failure = ensure_events(engine, scope.gpu_device)) return failure;
+
+    bool const symmetric = candidates_view.object == nullptr;
+    szs_b200_call_stats_t stats = {};
+    SZB_CUDA(cudaEventRecord(engine.events[0], stream));
+
+    // 1. Stage both sides.
+    if (Failure failure = stage_set(queries_view, engine.queries, stream, stats)) return failure;
+    StagedSet &qs = engine.queries;
+    if (!symmetric)
+        if (Failure failure = stage_set(candidates_view, engine.candidates, stream, stats)) return failure;
+    StagedSet &cs = symmetric ? engine.queries : engine.candidates;
+
+    size_t const n_queries = qs.count, n_candidates = cs.count;
+    if (whole_matrix) row_begin = 0, row_end = n_queries;
+    if (row_end > n_queries || row_begin > row_end) return fail(sz_unexpected_dimensions_k, "Row range out of bounds");
+    if (n_candidates && stride < n_candidates)
+        return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
+    size_t const n_rows = row_end - row_begin;
+    if (n_rows == 0 || n_candidates == 0) {
+        SZB_CUDA(cudaStreamSynchronize(stream));
+        engine.stats = stats;
+        return ok();
+    }
+    if (!results) return fail(sz_unexpected_dimensions_k, "Results pointer is null");
+    if (n_queries >= 0xFFFFFFF0ull || n_candidates >= 0xFFFFFFF0ull)
+        return fail(sz_overflow_risk_k, "Too many strings for one call");
+
+    trace.mark("staged");
+    // 2. Which symbols are we scoring: byte presence for the Levenshtein alphabet, UTF-8 decoding / rune ranking.
+    uint32_t present[256] = {0};
+    bool wide_symbols = false;
+    if (Failure failure = resolve_symbols(engine, stream, symmetric, qs, cs, stats, present, wide_symbols)) return failure;
     trace.mark("alphabet known");
     Model model;
     build_model(engine, present, wide_symbols, model);
