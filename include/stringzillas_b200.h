@@ -305,6 +305,17 @@ SZS_B200_API sz_status_t szs_b200_last_call_stats(void const *engine, szs_b200_c
  *  measure that tier on the headline workload). Results are identical either way. */
 SZS_B200_API sz_status_t szs_b200_set_bit_parallel(void *engine, int enabled);
 
+/** Diagnostics / unit tests of the host scheduler (no GPU needed): runs the planning steps of a call on string LENGTHS
+ *  alone and reports, per candidate, `assignment` = tier (bits 0-7: 0 bit-parallel, 1 packed int16 DP, 2 32-bit DP) |
+ *  words-per-lane or strip width (bits 8-15) | lanes (bits 16-23) | family (bits 24-31), its slot `partner` (or
+ *  0xFFFFFFFF), the longest-first query `order`, and the DP jobs as (first candidate of the slot, q_begin, q_end)
+ *  triples. `candidate_lengths == NULL` plans the symmetric self-similarity of the queries. */
+SZS_B200_API sz_status_t szs_b200_debug_schedule(void const *engine, sz_u32_t const *query_lengths, sz_size_t n_queries,
+                                                 sz_u32_t const *candidate_lengths, sz_size_t n_candidates,
+                                                 int distinct_candidate_bytes, int device_sms, sz_u32_t *assignment,
+                                                 sz_u32_t *partner, sz_u32_t *order, sz_u32_t *jobs,
+                                                 sz_size_t jobs_capacity, sz_size_t *n_jobs);
+
 /** Score only query rows [row_begin, row_end) of the cross product; `results` still addresses the FULL matrix
  *  (`results[q * stride + c]`), rows outside the range are left untouched. This is the shard primitive of the
  *  multi-GPU partition: each rank owns a contiguous block of query rows balanced by total query length.

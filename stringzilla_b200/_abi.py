@@ -112,7 +112,8 @@ REFERENCE_SYMBOLS = [
     "szs_fingerprints_init", "szs_fingerprints_sequence", "szs_fingerprints_u32tape", "szs_fingerprints_u64tape",
     "szs_fingerprints_free",
 ]  # fmt: skip
-B200_SYMBOLS = ["szs_b200_last_call_stats", "szs_b200_scores_u64tape_rows", "szs_b200_set_bit_parallel"]
+B200_SYMBOLS = ["szs_b200_last_call_stats", "szs_b200_scores_u64tape_rows", "szs_b200_set_bit_parallel",
+                "szs_b200_debug_schedule"]
 
 
 def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
@@ -166,6 +167,8 @@ def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
         lib.szs_b200_scores_u64tape_rows.restype = ct.c_int
         lib.szs_b200_set_bit_parallel.argtypes = [vp, ct.c_int]
         lib.szs_b200_set_bit_parallel.restype = ct.c_int
+        lib.szs_b200_debug_schedule.argtypes = [vp, vp, u64, vp, u64, ct.c_int, ct.c_int, vp, vp, vp, vp, u64, ct.POINTER(u64)]
+        lib.szs_b200_debug_schedule.restype = ct.c_int
     return lib
 
 

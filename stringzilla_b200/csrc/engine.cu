@@ -861,6 +861,265 @@ struct Trace {
     }
 };
 
+/** A candidate pair (or single) of the DP tiers with the recurrence family and strip shape chosen for it. */
+struct HostSlot {
+    CandSlot slot;
+    int family;
+    Shape shape;
+};
+
+/** The candidates one bit-parallel launch covers (all with the same number of pattern words per lane). */
+struct MyersLaunch {
+    int words;
+    std::vector<MyersCandidate> members; // longest first
+};
+
+/** Everything the host decides about one call before anything is launched; pure host data (unit-testable). */
+struct Schedule {
+    std::vector<uint32_t> order;    ///< query rows of this call, longest first
+    std::vector<uint32_t> position; ///< inverse of `order` (symmetric triangle only)
+    bool triangle = false;          ///< symmetric call under symmetric costs: each unordered pair scored once
+    std::vector<HostSlot> slots;    ///< DP tiers
+    std::vector<Job> jobs;          ///< DP tiers: slot x block of the query order, grouped by plan
+    std::vector<LaunchPlan> plans;  ///< DP tiers: one launch per (family, strip width)
+    uint64_t scratch_words_per_cta = 0;
+    std::vector<MyersLaunch> myers_launches; ///< bit-parallel tier, heaviest launch first
+    bool myers_shared_table = false;
+    int myers_rows = 0;
+    uint64_t cells_total = 0, cells_u16 = 0, cells_myers = 0;
+};
+
+/**
+ *  @brief Steps 4-6 of a call: order the queries, split the candidates between the bit-parallel tier and the DP tiers,
+ *         pair DP candidates into slots, choose shapes, and cut everything into jobs / tasks. Host-only.
+ */
+static Failure build_schedule(Engine const &engine, Model const &model, StagedSet const &qs, StagedSet const &cs,
+                              bool symmetric, bool whole_matrix, size_t row_begin, size_t n_rows,
+                              uint32_t const (&present)[256], bool wide_symbols, int device_sms, Trace const &trace,
+                              Schedule &schedule) {
+    size_t const n_queries = qs.count, n_candidates = cs.count;
+    // 4. Query order: longest first, so that the batches a warp sweeps together have similar lengths and the heavy
+    //    jobs start early.
+    auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
+    std::vector<uint32_t> &order = schedule.order;
+    order.assign(n_rows, 0);
+    {   // One 64-bit key per string — (inverted length, index) — sorts stably with a plain integer sort.
+        std::vector<uint64_t> keys(n_rows);
+        for (size_t i = 0; i < n_rows; ++i) {
+            uint32_t const q = (uint32_t)(row_begin + i);
+            keys[i] = ((uint64_t)(0xFFFFFFFFu - query_length(q)) << 32) | q;
+        }
+        std::sort(keys.begin(), keys.end());
+        for (size_t i = 0; i < n_rows; ++i) order[i] = (uint32_t)keys[i];
+    }
+    uint32_t const longest_query = query_length(order[0]);
+
+    // Symmetric self-similarity under a symmetric cost model: score every unordered pair once, with the string that
+    // comes first in the longest-first order as the query. A candidate at position p then needs only the queries at
+    // positions [0, p] — a prefix of the order — and a ranked mirror fills the other half. (An asymmetric substitution
+    // table must follow the reference's (query = i, candidate = j <= i) orientation: full matrix + index mirror.)
+    bool const triangle = schedule.triangle = symmetric && whole_matrix && model.symmetric_costs && n_queries > 1;
+    std::vector<uint32_t> &position = schedule.position;
+    position.clear();
+    if (triangle) {
+        position.resize(n_queries);
+        for (uint32_t p = 0; p < (uint32_t)n_rows; ++p) position[order[p]] = p;
+    }
+    auto rows_needed = [&](uint32_t candidate) { return triangle ? position[candidate] + 1 : (uint32_t)n_rows; };
+
+    trace.mark("queries ordered");
+    // 5. Slots: candidates sorted by length; neighbours share a register in the packed tier.
+    auto candidate_length = [&](uint32_t c) { return cs.offsets[c + 1] - cs.offsets[c]; };
+    std::vector<uint32_t> by_length(n_candidates);
+    {
+        std::vector<uint64_t> keys(n_candidates);
+        for (size_t c = 0; c < n_candidates; ++c) keys[c] = ((uint64_t)candidate_length((uint32_t)c) << 32) | (uint32_t)c;
+        std::sort(keys.begin(), keys.end());
+        for (size_t c = 0; c < n_candidates; ++c) by_length[c] = (uint32_t)keys[c];
+    }
+
+    // 5a. Unit-cost Levenshtein over a compact alphabet: candidates the bit-parallel kernel covers leave the DP tiers.
+    std::vector<MyersLaunch> &myers_launches = schedule.myers_launches;
+    myers_launches.clear();
+    uint64_t &cells_myers = schedule.cells_myers = 0;
+    bool const unit_costs = engine.algorithm == Algorithm::kLevenshtein && engine.match == 0 && engine.mismatch == 1 &&
+                            engine.open == 1 && engine.extend == 1;
+    // Compact alphabets keep one match table per WARP (rows = classes); raw-byte alphabets of more than 31 symbols keep
+    // one table per CTA whose rows are the bytes the candidate contains (bounded by the bytes any candidate contains).
+    bool const myers_shared_table = schedule.myers_shared_table = model.scoring.compare != 0;
+    int &myers_rows = schedule.myers_rows = model.scoring.n_classes;
+    if (myers_shared_table) {
+        myers_rows = 1;
+        for (int b = 0; b < 256; ++b) myers_rows += present[b] != 0;
+    }
+    if (unit_costs && engine.bit_parallel && !wide_symbols) {
+        uint64_t query_bytes = 0;
+        for (uint32_t q : order) query_bytes += query_length(q);
+        std::vector<uint32_t> kept;
+        // Shared memory bounds the words per lane: a sixteenth of the SM per warp-private table (sixteen resident
+        // warps per CTA), or the whole carve-out for a CTA-shared one.
+        size_t const table_budget = myers_shared_table ? 220 * 1024 - 1024 : 12 * 1024;
+        int const max_words = (int)(table_budget / ((size_t)myers_rows * 32 * 4));
+        uint32_t remembered_length = 0xFFFFFFFFu;
+        int remembered_words = 0, remembered_lanes = 0;
+        MyersLaunch *remembered_launch = nullptr;
+        for (size_t i = n_candidates; i-- > 0;) { // longest first
+            uint32_t const c = by_length[i], length = candidate_length(c);
+            // Candidates arrive sorted by length: equal lengths are neighbours, so one remembered answer suffices.
+            if (length != remembered_length) {
+                myers_shape_for_length(length, max_words, remembered_words, remembered_lanes);
+                remembered_length = length;
+            }
+            int const words = remembered_words, lanes = remembered_lanes;
+            if (words == 0) {
+                kept.push_back(c);
+                continue;
+            }
+            if (!remembered_launch || remembered_launch->words != words) {
+                auto launch = std::find_if(myers_launches.begin(), myers_launches.end(),
+                                           [&](MyersLaunch const &l) { return l.words == words; });
+                if (launch == myers_launches.end()) {
+                    myers_launches.reserve(kMyersMaxWords); // keeps `remembered_launch` valid across push_backs
+                    myers_launches.push_back({words, {}}), launch = myers_launches.end() - 1;
+                }
+                remembered_launch = &*launch;
+            }
+            remembered_launch->members.push_back({c, (uint32_t)lanes, rows_needed(c)});
+            cells_myers += (uint64_t)length * query_bytes;
+        }
+        std::reverse(kept.begin(), kept.end()); // back to ascending length for the slot builder
+        by_length.swap(kept);
+    }
+    size_t const n_dp_candidates = by_length.size();
+    // A launch that cannot fill the GPU for ~50 us is folded into the next wider one: padding a few candidates to
+    // more words per lane costs less than a dependent launch of its own.
+    if (myers_launches.size() > 1) {
+        uint64_t query_bytes = 0;
+        for (uint32_t q : order) query_bytes += query_length(q);
+        std::sort(myers_launches.begin(), myers_launches.end(),
+                  [](MyersLaunch const &a, MyersLaunch const &b) { return a.words < b.words; });
+        for (size_t l = 0; l + 1 < myers_launches.size();) {
+            uint64_t cells = 0;
+            for (MyersCandidate const &member : myers_launches[l].members)
+                cells += (uint64_t)candidate_length(member.candidate) * query_bytes;
+            if (cells >= 1500000000ull) {
+                ++l;
+                continue;
+            }
+            MyersLaunch &wider = myers_launches[l + 1];
+            for (MyersCandidate member : myers_launches[l].members) {
+                uint32_t lanes = 1;
+                while (32u * wider.words * lanes < candidate_length(member.candidate)) lanes *= 2;
+                member.lanes = lanes;
+                wider.members.push_back(member);
+            }
+            myers_launches.erase(myers_launches.begin() + l);
+        }
+        for (MyersLaunch &launch : myers_launches)
+            std::stable_sort(launch.members.begin(), launch.members.end(), [&](MyersCandidate const &a, MyersCandidate const &b) {
+                return candidate_length(a.candidate) > candidate_length(b.candidate);
+            });
+    }
+    // Heaviest launch first, so that the lighter ones fill the tail of the heavier ones.
+    auto launch_weight = [&](MyersLaunch const &launch) {
+        uint64_t weight = 0;
+        for (MyersCandidate const &member : launch.members) weight += candidate_length(member.candidate);
+        return weight;
+    };
+    std::sort(myers_launches.begin(), myers_launches.end(),
+              [&](MyersLaunch const &a, MyersLaunch const &b) { return launch_weight(a) > launch_weight(b); });
+
+    std::vector<HostSlot> &host_slots = schedule.slots;
+    host_slots.clear();
+    host_slots.reserve(n_dp_candidates);
+    uint64_t &cells_total = schedule.cells_total = 0, &cells_u16 = schedule.cells_u16 = 0;
+    uint64_t query_bytes_in_rows = 0;
+    for (uint32_t q : order) query_bytes_in_rows += query_length(q);
+    // Register budget (128 per thread) caps the strip width per family: packed affine recurrences keep two strips per
+    // lane (36 columns), the 32-bit tier adds the strip's symbols for compare mode (32 linear / 20 affine).
+    auto widest_strip = [](int family) {
+        if (family == FAM_LIN_COMPARE) return 32; // strip cells + strip bytes
+        if (family >= FAM_S32_GLOBAL_LIN) return family_is_affine(family) ? 20 : 32;
+        return family_is_affine(family) ? 36 : 40;
+    };
+    auto shape_of = [&](int family, uint32_t longest) {
+        Shape shape = shape_for_length(longest);
+        int const cap = widest_strip(family);
+        if (kStrips[shape.strip_index] > cap) {
+            uint32_t const widest = (uint32_t)cap * 32;
+            uint32_t const passes = (longest + widest - 1) / widest, width = (longest + passes - 1) / passes;
+            for (int i = 0; i < kStripCount; ++i)
+                if ((uint32_t)kStrips[i] * 32 >= width) return Shape {i, 32};
+        }
+        return shape;
+    };
+    for (size_t i = 0; i < n_dp_candidates;) {
+        uint32_t const c0 = by_length[i], len0 = candidate_length(c0);
+        bool const narrow0 = fits_u16(model, std::min<uint64_t>(len0, longest_query));
+        if (narrow0 && i + 1 < n_dp_candidates) {
+            uint32_t const c1 = by_length[i + 1], len1 = candidate_length(c1);
+            if (fits_u16(model, std::min<uint64_t>(len1, longest_query))) {
+                host_slots.push_back({{c0, c1, len0, len1}, model.family16, shape_of(model.family16, len1)});
+                cells_u16 += ((uint64_t)len0 + len1) * query_bytes_in_rows;
+                i += 2;
+                continue;
+            }
+        }
+        int const family = narrow0 ? model.family16 : model.family32;
+        host_slots.push_back({{c0, kNoCandidate, len0, 0}, family, shape_of(family, len0)});
+        if (narrow0) cells_u16 += (uint64_t)len0 * query_bytes_in_rows;
+        i += 1;
+    }
+    for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
+
+    trace.mark("slots built");
+    // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
+    std::vector<Job> &host_jobs = schedule.jobs;
+    std::vector<LaunchPlan> &plans = schedule.plans;
+    host_jobs.clear(), plans.clear();
+    uint64_t &scratch_words_per_cta = schedule.scratch_words_per_cta = 0;
+    for (int family = 0; family < kFamilyCount; ++family) {
+        for (int strip = kStripCount - 1; strip >= 0; --strip) {
+            // Longest slots first: their jobs are the heaviest, and the atomic job counter hands them out in order.
+            std::vector<uint32_t> members;
+            for (uint32_t s = (uint32_t)host_slots.size(); s-- > 0;)
+                if (host_slots[s].family == family && host_slots[s].shape.strip_index == strip) members.push_back(s);
+            if (members.empty()) continue;
+            LaunchPlan plan = {family, strip, (uint32_t)host_jobs.size(), 0};
+            bool const affine = family_is_affine(family);
+            uint64_t const target_jobs = (uint64_t)device_sms * 8;
+            uint64_t const wanted_blocks = (target_jobs + members.size() - 1) / members.size();
+            for (uint32_t s : members) {
+                CandSlot const &slot = host_slots[s].slot;
+                Shape const shape = host_slots[s].shape;
+                // A block is a whole number of rounds of the CTA's warps (each sweeps 32 / G queries at a time),
+                // so that no warp idles at the job's barrier while others run an extra round.
+                uint32_t const round = (uint32_t)(kThreads / 32) * (32 / shape.lanes);
+                uint32_t const slot_rows =
+                    std::max(rows_needed(slot.c0), slot.c1 != kNoCandidate ? rows_needed(slot.c1) : 0u);
+                uint64_t const rounds_total = (slot_rows + round - 1) / round;
+                uint64_t const blocks = std::max<uint64_t>(1, std::min<uint64_t>(wanted_blocks, rounds_total));
+                uint32_t const block_rows = (uint32_t)((rounds_total + blocks - 1) / blocks) * round;
+                uint32_t const longest = std::max(slot.len0, slot.len1);
+                for (uint32_t begin = 0; begin < slot_rows; begin += block_rows) {
+                    uint32_t const end = (uint32_t)std::min<uint64_t>(slot_rows, (uint64_t)begin + block_rows);
+                    if (longest > (uint32_t)shape.coverage()) {
+                        uint64_t const rows = (uint64_t)query_length(order[begin]) + 1;
+                        uint64_t const words = (uint64_t)(end - begin) * rows * (affine ? 2 : 1);
+                        if (words > 0xFFFFFFFFull) return fail(sz_overflow_risk_k, "Boundary scratch too large");
+                        scratch_words_per_cta = std::max<uint64_t>(scratch_words_per_cta, words);
+                    }
+                    host_jobs.push_back({s, begin, end, (uint32_t)shape.lanes});
+                }
+            }
+            plan.n_jobs = (uint32_t)host_jobs.size() - plan.first_job;
+            plans.push_back(plan);
+        }
+    }
+
+    return ok();
+}
+
 static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
                      size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
     Trace const trace;
@@ -948,230 +1207,23 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     }
 
     trace.mark("classes mapped (async)");
-    // 4. Query order: longest first, so that the batches a warp sweeps together have similar lengths and the heavy
-    //    jobs start early.
-    auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
-    std::vector<uint32_t> order(n_rows);
-    {   // One 64-bit key per string — (inverted length, index) — sorts stably with a plain integer sort.
-        std::vector<uint64_t> keys(n_rows);
-        for (size_t i = 0; i < n_rows; ++i) {
-            uint32_t const q = (uint32_t)(row_begin + i);
-            keys[i] = ((uint64_t)(0xFFFFFFFFu - query_length(q)) << 32) | q;
-        }
-        std::sort(keys.begin(), keys.end());
-        for (size_t i = 0; i < n_rows; ++i) order[i] = (uint32_t)keys[i];
-    }
-    uint32_t const longest_query = query_length(order[0]);
-
-    // Symmetric self-similarity under a symmetric cost model: score every unordered pair once, with the string that
-    // comes first in the longest-first order as the query. A candidate at position p then needs only the queries at
-    // positions [0, p] — a prefix of the order — and a ranked mirror fills the other half. (An asymmetric substitution
-    // table must follow the reference's (query = i, candidate = j <= i) orientation: full matrix + index mirror.)
-    bool const triangle = symmetric && whole_matrix && model.symmetric_costs && n_queries > 1;
-    std::vector<uint32_t> position;
-    if (triangle) {
-        position.resize(n_queries);
-        for (uint32_t p = 0; p < (uint32_t)n_rows; ++p) position[order[p]] = p;
-    }
-    auto rows_needed = [&](uint32_t candidate) { return triangle ? position[candidate] + 1 : (uint32_t)n_rows; };
-
-    trace.mark("queries ordered");
-    // 5. Slots: candidates sorted by length; neighbours share a register in the packed tier.
-    auto candidate_length = [&](uint32_t c) { return cs.offsets[c + 1] - cs.offsets[c]; };
-    std::vector<uint32_t> by_length(n_candidates);
-    {
-        std::vector<uint64_t> keys(n_candidates);
-        for (size_t c = 0; c < n_candidates; ++c) keys[c] = ((uint64_t)candidate_length((uint32_t)c) << 32) | (uint32_t)c;
-        std::sort(keys.begin(), keys.end());
-        for (size_t c = 0; c < n_candidates; ++c) by_length[c] = (uint32_t)keys[c];
-    }
-
-    // 5a. Unit-cost Levenshtein over a compact alphabet: candidates the bit-parallel kernel covers leave the DP tiers.
-    struct MyersLaunch {
-        int words;
-        std::vector<MyersCandidate> members; // longest first
-    };
-    std::vector<MyersLaunch> myers_launches;
-    uint64_t cells_myers = 0;
-    bool const unit_costs = engine.algorithm == Algorithm::kLevenshtein && engine.match == 0 && engine.mismatch == 1 &&
-                            engine.open == 1 && engine.extend == 1;
-    // Compact alphabets keep one match table per WARP (rows = classes); raw-byte alphabets of more than 31 symbols keep
-    // one table per CTA whose rows are the bytes the candidate contains (bounded by the bytes any candidate contains).
-    bool const myers_shared_table = model.scoring.compare != 0;
-    int myers_rows = model.scoring.n_classes;
-    if (myers_shared_table) {
-        myers_rows = 1;
-        for (int b = 0; b < 256; ++b) myers_rows += present[b] != 0;
-    }
-    if (unit_costs && engine.bit_parallel && !wide_symbols) {
-        uint64_t query_bytes = 0;
-        for (uint32_t q : order) query_bytes += query_length(q);
-        std::vector<uint32_t> kept;
-        // Shared memory bounds the words per lane: a sixteenth of the SM per warp-private table (sixteen resident
-        // warps per CTA), or the whole carve-out for a CTA-shared one.
-        size_t const table_budget = myers_shared_table ? 220 * 1024 - 1024 : 12 * 1024;
-        int const max_words = (int)(table_budget / ((size_t)myers_rows * 32 * 4));
-        uint32_t remembered_length = 0xFFFFFFFFu;
-        int remembered_words = 0, remembered_lanes = 0;
-        MyersLaunch *remembered_launch = nullptr;
-        for (size_t i = n_candidates; i-- > 0;) { // longest first
-            uint32_t const c = by_length[i], length = candidate_length(c);
-            // Candidates arrive sorted by length: equal lengths are neighbours, so one remembered answer suffices.
-            if (length != remembered_length) {
-                myers_shape_for_length(length, max_words, remembered_words, remembered_lanes);
-                remembered_length = length;
-            }
-            int const words = remembered_words, lanes = remembered_lanes;
-            if (words == 0) {
-                kept.push_back(c);
-                continue;
-            }
-            if (!remembered_launch || remembered_launch->words != words) {
-                auto launch = std::find_if(myers_launches.begin(), myers_launches.end(),
-                                           [&](MyersLaunch const &l) { return l.words == words; });
-                if (launch == myers_launches.end()) {
-                    myers_launches.reserve(kMyersMaxWords); // keeps `remembered_launch` valid across push_backs
-                    myers_launches.push_back({words, {}}), launch = myers_launches.end() - 1;
-                }
-                remembered_launch = &*launch;
-            }
-            remembered_launch->members.push_back({c, (uint32_t)lanes, rows_needed(c)});
-            cells_myers += (uint64_t)length * query_bytes;
-        }
-        std::reverse(kept.begin(), kept.end()); // back to ascending length for the slot builder
-        by_length.swap(kept);
-    }
-    size_t const n_dp_candidates = by_length.size();
-    // A launch that cannot fill the GPU for ~50 us is folded into the next wider one: padding a few candidates to
-    // more words per lane costs less than a dependent launch of its own.
-    if (myers_launches.size() > 1) {
-        uint64_t query_bytes = 0;
-        for (uint32_t q : order) query_bytes += query_length(q);
-        std::sort(myers_launches.begin(), myers_launches.end(),
-                  [](MyersLaunch const &a, MyersLaunch const &b) { return a.words < b.words; });
-        for (size_t l = 0; l + 1 < myers_launches.size();) {
-            uint64_t cells = 0;
-            for (MyersCandidate const &member : myers_launches[l].members)
-                cells += (uint64_t)candidate_length(member.candidate) * query_bytes;
-            if (cells >= 1500000000ull) {
-                ++l;
-                continue;
-            }
-            MyersLaunch &wider = myers_launches[l + 1];
-            for (MyersCandidate member : myers_launches[l].members) {
-                uint32_t lanes = 1;
-                while (32u * wider.words * lanes < candidate_length(member.candidate)) lanes *= 2;
-                member.lanes = lanes;
-                wider.members.push_back(member);
-            }
-            myers_launches.erase(myers_launches.begin() + l);
-        }
-        for (MyersLaunch &launch : myers_launches)
-            std::stable_sort(launch.members.begin(), launch.members.end(), [&](MyersCandidate const &a, MyersCandidate const &b) {
-                return candidate_length(a.candidate) > candidate_length(b.candidate);
-            });
-    }
-    // Heaviest launch first, so that the lighter ones fill the tail of the heavier ones.
-    auto launch_weight = [&](MyersLaunch const &launch) {
-        uint64_t weight = 0;
-        for (MyersCandidate const &member : launch.members) weight += candidate_length(member.candidate);
-        return weight;
-    };
-    std::sort(myers_launches.begin(), myers_launches.end(),
-              [&](MyersLaunch const &a, MyersLaunch const &b) { return launch_weight(a) > launch_weight(b); });
-
-    struct HostSlot {
-        CandSlot slot;
-        int family;
-        Shape shape;
-    };
-    std::vector<HostSlot> host_slots;
-    host_slots.reserve(n_dp_candidates);
-    uint64_t cells_total = 0, cells_u16 = 0;
-    uint64_t query_bytes_in_rows = 0;
-    for (uint32_t q : order) query_bytes_in_rows += query_length(q);
-    // Register budget (128 per thread) caps the strip width per family: packed affine recurrences keep two strips per
-    // lane (36 columns), the 32-bit tier adds the strip's symbols for compare mode (32 linear / 20 affine).
-    auto widest_strip = [](int family) {
-        if (family == FAM_LIN_COMPARE) return 32; // strip cells + strip bytes
-        if (family >= FAM_S32_GLOBAL_LIN) return family_is_affine(family) ? 20 : 32;
-        return family_is_affine(family) ? 36 : 40;
-    };
-    auto shape_of = [&](int family, uint32_t longest) {
-        Shape shape = shape_for_length(longest);
-        int const cap = widest_strip(family);
-        if (kStrips[shape.strip_index] > cap) {
-            uint32_t const widest = (uint32_t)cap * 32;
-            uint32_t const passes = (longest + widest - 1) / widest, width = (longest + passes - 1) / passes;
-            for (int i = 0; i < kStripCount; ++i)
-                if ((uint32_t)kStrips[i] * 32 >= width) return Shape {i, 32};
-        }
-        return shape;
-    };
-    for (size_t i = 0; i < n_dp_candidates;) {
-        uint32_t const c0 = by_length[i], len0 = candidate_length(c0);
-        bool const narrow0 = fits_u16(model, std::min<uint64_t>(len0, longest_query));
-        if (narrow0 && i + 1 < n_dp_candidates) {
-            uint32_t const c1 = by_length[i + 1], len1 = candidate_length(c1);
-            if (fits_u16(model, std::min<uint64_t>(len1, longest_query))) {
-                host_slots.push_back({{c0, c1, len0, len1}, model.family16, shape_of(model.family16, len1)});
-                cells_u16 += ((uint64_t)len0 + len1) * query_bytes_in_rows;
-                i += 2;
-                continue;
-            }
-        }
-        int const family = narrow0 ? model.family16 : model.family32;
-        host_slots.push_back({{c0, kNoCandidate, len0, 0}, family, shape_of(family, len0)});
-        if (narrow0) cells_u16 += (uint64_t)len0 * query_bytes_in_rows;
-        i += 1;
-    }
-    for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
-
-    trace.mark("slots built");
-    // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
+    // 4-6. The schedule: query order, bit-parallel candidates, DP slots and shapes, jobs (pure host work).
     int const device_sms = std::max(1, device_facts(scope.gpu_device).sms);
-    std::vector<Job> host_jobs;
-    std::vector<LaunchPlan> plans;
-    uint64_t scratch_words_per_cta = 0;
-    for (int family = 0; family < kFamilyCount; ++family) {
-        for (int strip = kStripCount - 1; strip >= 0; --strip) {
-            // Longest slots first: their jobs are the heaviest, and the atomic job counter hands them out in order.
-            std::vector<uint32_t> members;
-            for (uint32_t s = (uint32_t)host_slots.size(); s-- > 0;)
-                if (host_slots[s].family == family && host_slots[s].shape.strip_index == strip) members.push_back(s);
-            if (members.empty()) continue;
-            LaunchPlan plan = {family, strip, (uint32_t)host_jobs.size(), 0};
-            bool const affine = family_is_affine(family);
-            uint64_t const target_jobs = (uint64_t)device_sms * 8;
-            uint64_t const wanted_blocks = (target_jobs + members.size() - 1) / members.size();
-            for (uint32_t s : members) {
-                CandSlot const &slot = host_slots[s].slot;
-                Shape const shape = host_slots[s].shape;
-                // A block is a whole number of rounds of the CTA's warps (each sweeps 32 / G queries at a time),
-                // so that no warp idles at the job's barrier while others run an extra round.
-                uint32_t const round = (uint32_t)(kThreads / 32) * (32 / shape.lanes);
-                uint32_t const slot_rows =
-                    std::max(rows_needed(slot.c0), slot.c1 != kNoCandidate ? rows_needed(slot.c1) : 0u);
-                uint64_t const rounds_total = (slot_rows + round - 1) / round;
-                uint64_t const blocks = std::max<uint64_t>(1, std::min<uint64_t>(wanted_blocks, rounds_total));
-                uint32_t const block_rows = (uint32_t)((rounds_total + blocks - 1) / blocks) * round;
-                uint32_t const longest = std::max(slot.len0, slot.len1);
-                for (uint32_t begin = 0; begin < slot_rows; begin += block_rows) {
-                    uint32_t const end = (uint32_t)std::min<uint64_t>(slot_rows, (uint64_t)begin + block_rows);
-                    if (longest > (uint32_t)shape.coverage()) {
-                        uint64_t const rows = (uint64_t)query_length(order[begin]) + 1;
-                        uint64_t const words = (uint64_t)(end - begin) * rows * (affine ? 2 : 1);
-                        if (words > 0xFFFFFFFFull) return fail(sz_overflow_risk_k, "Boundary scratch too large");
-                        scratch_words_per_cta = std::max<uint64_t>(scratch_words_per_cta, words);
-                    }
-                    host_jobs.push_back({s, begin, end, (uint32_t)shape.lanes});
-                }
-            }
-            plan.n_jobs = (uint32_t)host_jobs.size() - plan.first_job;
-            plans.push_back(plan);
-        }
-    }
-
+    Schedule schedule;
+    if (Failure failure = build_schedule(engine, model, qs, cs, symmetric, whole_matrix, row_begin, n_rows, present,
+                                         wide_symbols, device_sms, trace, schedule))
+        return failure;
+    std::vector<uint32_t> const &order = schedule.order, &position = schedule.position;
+    bool const triangle = schedule.triangle;
+    std::vector<HostSlot> const &host_slots = schedule.slots;
+    std::vector<Job> const &host_jobs = schedule.jobs;
+    std::vector<LaunchPlan> const &plans = schedule.plans;
+    std::vector<MyersLaunch> const &myers_launches = schedule.myers_launches;
+    bool const myers_shared_table = schedule.myers_shared_table;
+    int const myers_rows = schedule.myers_rows;
+    uint64_t const scratch_words_per_cta = schedule.scratch_words_per_cta;
+    uint64_t const cells_total = schedule.cells_total, cells_u16 = schedule.cells_u16, cells_myers = schedule.cells_myers;
+    auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
     trace.mark("jobs built");
     // 7. Upload the work list.
     std::vector<CandSlot> device_slots(host_slots.size());
@@ -1623,6 +1675,55 @@ SZS_B200_API void szs_fingerprints_free(szs_fingerprints_t) {}
 SZS_B200_API sz_status_t szs_b200_last_call_stats(void const *engine, szs_b200_call_stats_t *stats) {
     if (!engine || !stats) return sz_status_unknown_k;
     *stats = static_cast<Engine const *>(engine)->stats;
+    return sz_success_k;
+}
+
+SZS_B200_API sz_status_t szs_b200_debug_schedule(void const *engine_punned, sz_u32_t const *query_lengths,
+                                                 sz_size_t n_queries, sz_u32_t const *candidate_lengths,
+                                                 sz_size_t n_candidates, int distinct_candidate_bytes, int device_sms,
+                                                 sz_u32_t *assignment, sz_u32_t *partner, sz_u32_t *order,
+                                                 sz_u32_t *jobs, sz_size_t jobs_capacity, sz_size_t *n_jobs) {
+    if (!engine_punned || !query_lengths || !assignment || !partner || !order || !n_jobs) return sz_status_unknown_k;
+    auto const &engine = *static_cast<Engine const *>(engine_punned);
+    bool const symmetric = candidate_lengths == nullptr;
+    szb::StagedSet qs, cs_storage;
+    auto fill = [](szb::StagedSet &set, sz_u32_t const *lengths, size_t count) {
+        set.count = count, set.offsets.assign(count + 1, 0), set.longest = 0;
+        for (size_t i = 0; i < count; ++i)
+            set.offsets[i + 1] = set.offsets[i] + lengths[i], set.longest = std::max(set.longest, lengths[i]);
+        set.total_bytes = set.offsets[count];
+    };
+    fill(qs, query_lengths, n_queries);
+    if (!symmetric) fill(cs_storage, candidate_lengths, n_candidates);
+    szb::StagedSet const &cs = symmetric ? qs : cs_storage;
+    if (qs.count == 0 || cs.count == 0) return sz_unexpected_dimensions_k;
+    uint32_t present[256] = {0};
+    for (int b = 0; b < 256 && b < distinct_candidate_bytes; ++b) present[b] = 1;
+    szb::Model model;
+    szb::build_model(engine, present, false, model);
+    szb::Schedule schedule;
+    szb::Trace const trace;
+    szb::Failure failure = szb::build_schedule(engine, model, qs, cs, symmetric, true, 0, qs.count, present, false,
+                                               std::max(device_sms, 1), trace, schedule);
+    if (failure) return failure.status;
+    for (size_t c = 0; c < cs.count; ++c) assignment[c] = 0xFFFFFFFFu, partner[c] = 0xFFFFFFFFu;
+    for (szb::MyersLaunch const &launch : schedule.myers_launches)
+        for (szb::MyersCandidate const &member : launch.members)
+            assignment[member.candidate] = 0u | ((uint32_t)launch.words << 8) | (member.lanes << 16) | (member.rows ? 0u : 0u);
+    for (szb::HostSlot const &host : schedule.slots) {
+        uint32_t const tier = host.family >= szb::FAM_S32_GLOBAL_LIN && host.family <= szb::FAM_S32_LOCAL_AFF ? 2u : 1u;
+        uint32_t const code = tier | ((uint32_t)szb::kStrips[host.shape.strip_index] << 8) | ((uint32_t)host.shape.lanes << 16) |
+                              ((uint32_t)host.family << 24);
+        assignment[host.slot.c0] = code;
+        if (host.slot.c1 != szb::kNoCandidate)
+            assignment[host.slot.c1] = code, partner[host.slot.c0] = host.slot.c1, partner[host.slot.c1] = host.slot.c0;
+    }
+    for (size_t i = 0; i < schedule.order.size(); ++i) order[i] = schedule.order[i];
+    *n_jobs = schedule.jobs.size();
+    for (size_t j = 0; j < schedule.jobs.size() && j < jobs_capacity; ++j) {
+        jobs[3 * j] = schedule.slots[schedule.jobs[j].slot].slot.c0;
+        jobs[3 * j + 1] = schedule.jobs[j].q_begin, jobs[3 * j + 2] = schedule.jobs[j].q_end;
+    }
     return sz_success_k;
 }
 
