@@ -377,6 +377,48 @@ def test_c_program_against_the_reference_header(scope):
     assert ran.returncode == 0 and "status 0 distance 3" in ran.stdout, ran.stdout + ran.stderr
 
 
+def test_memory_kinds_and_tape_slices(scope):
+    """Inputs and outputs in device memory, in managed memory (`szs_unified_alloc`, what the reference's Python binding
+    uses), and tapes whose first offset is not zero (a slice of a larger Arrow array)."""
+    import torch
+
+    rng = np.random.default_rng(53)
+    strings = support.random_strings(rng, 14, 0, 200, support.PROTEIN)
+    whole = szb.Tape(strings)
+    byte_to_class, table = scoring.blosum62()
+    engine = szb.NeedlemanWunschScores(byte_to_class, table, open=-4, extend=-1)
+    lib = _abi.bind()
+    message = ct.c_char_p()
+    # Queries = strings[3:9], candidates = strings[5:14], both as windows into the SAME blob with non-zero first offsets.
+    q_offsets, c_offsets = whole.offsets[3:10].copy(), whole.offsets[5:15].copy()
+    want = support.oracle_weighted(strings[3:9], strings[5:14], byte_to_class, table, -4, -1, False)
+
+    def call(data_pointer, out_pointer):
+        tq = _abi.SequenceU64Tape(data_pointer, q_offsets.ctypes.data, 6)
+        tc = _abi.SequenceU64Tape(data_pointer, c_offsets.ctypes.data, 9)
+        status = lib.szs_needleman_wunsch_scores_u64tape(engine._handle, scope.handle, ct.byref(tq), ct.byref(tc),
+                                                         out_pointer, 9, ct.byref(message))
+        assert status == 0, message.value
+
+    host_out = np.zeros((6, 9), dtype=np.int64)
+    call(whole.data.ctypes.data, host_out.ctypes.data)
+    assert np.array_equal(host_out, want)
+
+    device_data = torch.from_numpy(whole.data).cuda()
+    device_out = torch.zeros((6, 9), dtype=torch.int64, device="cuda")
+    call(device_data.data_ptr(), device_out.data_ptr())
+    assert np.array_equal(device_out.cpu().numpy(), want)
+
+    managed = lib.szs_unified_alloc(int(whole.data.size))
+    managed_out = lib.szs_unified_alloc(6 * 9 * 8)
+    ct.memmove(managed, whole.data.ctypes.data, int(whole.data.size))
+    call(managed, managed_out)
+    got = np.frombuffer((ct.c_int64 * 54).from_address(managed_out), dtype=np.int64).reshape(6, 9)
+    assert np.array_equal(got, want)
+    lib.szs_unified_free(managed, int(whole.data.size))
+    lib.szs_unified_free(managed_out, 6 * 9 * 8)
+
+
 def test_row_shards_reassemble_the_matrix(scope):
     rng = np.random.default_rng(23)
     queries = support.random_strings(rng, 13, 0, 200, support.DNA)
