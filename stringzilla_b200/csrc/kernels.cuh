@@ -11,7 +11,7 @@
  *  A "slot" is a pair of candidates (c0, c1) of similar length whose DP cells travel together as the low / high
  *  16-bit halves of one 32-bit register, so that every DPX instruction (VIMNMX3.U16x2 / VIADDMNMX.U16x2) retires two
  *  independent cells. A "job" is a slot x a block of queries. A persistent CTA pulls jobs from an atomic counter;
- *  for each job (and each 1024-column pass of long candidates) it
+ *  for each job (and each pass of K * G columns, for candidates longer than the widest shape) it
  *    1. builds the slot's *substitution profile* in shared memory: prof[a][j] = packed (e(a, c0[j]), e(a, c1[j]))
  *       for every row class `a` — so the inner loop never compares characters or touches the 32x32 cost table,
  *    2. lets each warp (or sub-warp group of G lanes) sweep one query over the profile: lane `l` owns K consecutive
@@ -20,8 +20,9 @@
  *  K is a template parameter (the strip lives in registers), G is a run-time property of the job: the host picks
  *  the (K, G) whose coverage K * G fits the slot's length most tightly, because the cost of a sweep is proportional
  *  to K * G, not to the candidate's length.
- *  Profile rows are vector-interleaved ([vector v][lane l] -> 16 bytes) so that the LDS.128 of the 8 lanes of a
- *  quarter-warp covers all 32 banks whatever rows (classes) the lanes are reading: conflict-free by construction.
+ *  Profile rows are laid out [vector v][32 strip slots][16 bytes]: lane `l` reads its v-th vector at the compile-time
+ *  offset v * 512, and the LDS.128 of the 8 lanes of a quarter-warp covers all 32 banks whatever rows (classes) the
+ *  lanes are reading: conflict-free by construction.
  *
  *  Recurrences (all MAXIMISING; Levenshtein runs with negated costs and a negated result)
  *  --------------------------------------------------------------------------------------
@@ -36,9 +37,11 @@
  *  FAM_SW_LIN / FAM_SW_AFF (Smith-Waterman): unshifted, cells biased by B so every half stays non-negative and a
  *      plain 32-bit add of an arithmetically packed (possibly negative) profile entry is exact per half.
  *      Reference test/similarities.cuh:103-133, 234-280.
+ *  FAM_LIN_COMPARE  FAM_LIN_SHIFT for raw-byte alphabets of more than 31 symbols: the substitution term comes from a
+ *      packed XOR of the strip's bytes (kept in registers) with the row byte instead of a profile read.
  *  FAM_S32_*      one candidate per register, signed 32-bit cells, literal baseline recurrences with DPX s32 ops;
- *      serves pairs whose scores do not fit 16 bits, unusual cost signs, and Levenshtein over alphabets of more than
- *      31 distinct bytes (compare mode: the substitution is a byte comparison instead of a profile lookup).
+ *      serves pairs whose scores do not fit 16 bits, unusual cost signs, affine-gap Levenshtein over large alphabets
+ *      and UTF-32 symbol streams (compare mode: the substitution is a symbol comparison instead of a profile lookup).
  */
 #pragma once
 #include <cuda_runtime.h>
