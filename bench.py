@@ -445,7 +445,11 @@ def run_ours(args):
             "metric": "GCUPS (giga cell-updates/s), batched Levenshtein at |s|~1024" if args.workload == "c2" else f"GCUPS, {family}",
             "value": round(value, 1), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(resident_seconds * 1e3 / args.steps, 4), "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None,
+            # BASELINE.md §1 publishes one figure for this metric: the reference's own CUDA path on an H100 at 1000 bytes.
+            "vs_baseline": round(value / world / 5910.8, 3) if args.workload == "c2" else None,
+            "vs_baseline_note": ("per-GPU value / 5910.8 GCUPS = the reference's published H100 figure for 1000-byte unit-cost "
+                                 "Levenshtein (include/stringzillas/similarities/README.md:35); other hardware. Same box: "
+                                 "profiles/r1_reference_cuda_same_box.jsonl") if args.workload == "c2" else None,
             "dtype": ("u32 bit-vectors (bit-parallel)" if last_stats.pairs_bit_parallel else
                       "u16x2 (packed int16 DPX cells)" if last_stats.pairs_u16 else "s32"),
             "data": "synthetic", "impl": "ours",
