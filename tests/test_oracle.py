@@ -69,6 +69,13 @@ def test_oracle_matches_live_reference_on_random_batches(seed):
     for costs in ([0, 1, 1, 1], [1, 3, 3, 3], [1, 3, 4, 2], [0, 7, 2, 2]):
         got = szb.LevenshteinDistances(*costs, library_path=ref)(queries, candidates, device=scope)
         assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs)), costs
+    alphabet = list("abcdefgh абвгдежз αβγδεζηθ 数据科学机器 🙂🌍🚀💖")
+    text = lambda n: "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=n)).encode()
+    utf8_q = [text(int(n)) for n in rng.integers(0, 200, size=8)]
+    utf8_c = [text(int(n)) for n in rng.integers(0, 300, size=7)]
+    for costs in ([0, 1, 1, 1], [1, 3, 3, 3], [0, 4, 3, 2]):
+        got = szb.LevenshteinDistancesUTF8(*costs, library_path=ref)(utf8_q, utf8_c, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein_utf8(utf8_q, utf8_c, *costs)), costs
     byte_to_class, table = scoring.blosum62()
     proteins = support.random_strings(rng, 10, 0, 300, support.PROTEIN)
     others = support.mutated_copies(rng, proteins[:7], 0.3, support.PROTEIN)
