@@ -40,6 +40,10 @@ class Tape:
     def __init__(self, strings: "Iterable[bytes | str] | Tape | tuple[np.ndarray, np.ndarray]"):
         if isinstance(strings, Tape):
             self.data, self.offsets = strings.data, strings.offsets
+        elif _is_arrow_array(strings):
+            # Apache Arrow string / binary arrays ARE tapes (reference test/similarities.py:975-1005): the value buffer
+            # is used in place, the offsets (sliced arrays keep a non-zero first offset) are widened to 64 bits.
+            self.data, self.offsets = _arrow_buffers(strings)
         elif isinstance(strings, tuple) and len(strings) == 2 and isinstance(strings[0], np.ndarray):
             self.data = np.ascontiguousarray(strings[0], dtype=np.uint8)
             self.offsets = np.ascontiguousarray(strings[1], dtype=np.uint64)
@@ -66,6 +70,28 @@ class Tape:
 
     def pointer(self):
         return ct.byref(self._struct)
+
+
+def _is_arrow_array(value) -> bool:
+    module = type(value).__module__ or ""
+    return module.startswith("pyarrow") and hasattr(value, "buffers") and hasattr(value, "type")
+
+
+def _arrow_buffers(array):
+    import pyarrow as pa
+
+    if isinstance(array, pa.ChunkedArray):
+        array = array.combine_chunks()
+    if array.null_count:
+        raise ValueError("Arrow arrays with nulls are not supported: tapes hold non-NULL strings (stringzillas.h:75)")
+    wide = pa.types.is_large_string(array.type) or pa.types.is_large_binary(array.type)
+    if not (wide or pa.types.is_string(array.type) or pa.types.is_binary(array.type)):
+        raise TypeError(f"expected a string or binary Arrow array, got {array.type}")
+    _, offsets_buffer, data_buffer = array.buffers()
+    offsets = np.frombuffer(offsets_buffer, dtype=np.int64 if wide else np.int32)
+    offsets = offsets[array.offset : array.offset + len(array) + 1].astype(np.uint64)
+    data = np.frombuffer(data_buffer, dtype=np.uint8) if data_buffer is not None else np.zeros(1, dtype=np.uint8)
+    return data, offsets
 
 
 _libraries: dict = {}

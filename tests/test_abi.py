@@ -94,6 +94,20 @@ def test_reference_header_compiles_and_links_against_our_library(library_built, 
     assert "version 5.1.2" in ran.stdout
 
 
+def test_tape_from_arrow_arrays():
+    """Arrow string arrays are tapes already: value buffer used in place, slices keep their non-zero first offset."""
+    pa = pytest.importorskip("pyarrow")
+    words = ["", "alpha", "βήτα", "gamma", "", "delta"]
+    for array in (pa.array(words), pa.array(words, type=pa.large_string()), pa.array([w.encode() for w in words], type=pa.binary())):
+        tape = szb.Tape(array)
+        assert [tape[i] for i in range(len(tape))] == [w.encode() for w in words]
+        window = szb.Tape(array.slice(2, 3))
+        assert [window[i] for i in range(len(window))] == [w.encode() for w in words[2:5]]
+        assert int(window.offsets[0]) == len("alpha".encode()) and window.data.ctypes.data == tape.data.ctypes.data
+    with pytest.raises(ValueError):
+        szb.Tape(pa.array(["a", None]))
+
+
 def test_tape_packing():
     tape = szb.Tape([b"", b"abc", "é"])
     assert len(tape) == 3 and tape.offsets.tolist() == [0, 0, 3, 5]
