@@ -419,6 +419,23 @@ def test_memory_kinds_and_tape_slices(scope):
     lib.szs_unified_free(managed_out, 6 * 9 * 8)
 
 
+def test_arrow_arrays_as_inputs(scope):
+    """Arrow string arrays (and slices of them) go in as they are; same matrix as Python lists (reference
+    test/similarities.py:975-1005)."""
+    pa = pytest.importorskip("pyarrow")
+    rng = np.random.default_rng(59)
+    words = [w.decode() for w in support.random_strings(rng, 40, 0, 90, b"abcdefgh")]
+    engine = szb.LevenshteinDistances()
+    want = support.oracle_levenshtein([w.encode() for w in words[4:30]], [w.encode() for w in words[10:40]])
+    for kind in (pa.string(), pa.large_string()):
+        array = pa.array(words, type=kind)
+        got = engine(array.slice(4, 26), array.slice(10, 30), scope)
+        assert np.array_equal(got, want)
+    utf8 = szb.LevenshteinDistancesUTF8()
+    greek = ["αβγ", "αβ", "", "γβα", "abc"]
+    assert np.array_equal(utf8(pa.array(greek), None, scope), support.oracle_levenshtein_utf8([g.encode() for g in greek]))
+
+
 def test_row_shards_reassemble_the_matrix(scope):
     rng = np.random.default_rng(23)
     queries = support.random_strings(rng, 13, 0, 200, support.DNA)
