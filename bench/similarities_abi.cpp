@@ -44,6 +44,7 @@
 #include <string>
 #include <string_view>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "stringzillas_b200.h"
@@ -73,24 +74,28 @@ struct Library {
         return reinterpret_cast<signature_ *>(address);
     }
 
-    using init_levenshtein_t = sz_status_t(sz_error_cost_t, sz_error_cost_t, sz_error_cost_t, sz_error_cost_t,
-                                           sz_memory_allocator_t const *, sz_capability_t, void **, char const **);
-    using init_weighted_t = sz_status_t(sz_error_cost_t const *, sz_u8_t const *, sz_error_cost_t, sz_error_cost_t,
-                                        sz_memory_allocator_t const *, sz_capability_t, void **, char const **);
-    using call_t = sz_status_t(void *, szs_device_scope_t, sz_sequence_u64tape_t const *, sz_sequence_u64tape_t const *,
-                               void *, sz_size_t, char const **);
-    using free_t = void(void *);
+    // Every signature is taken from the header's own declaration, so an argument in the wrong place cannot compile.
+    using init_levenshtein_t = std::remove_pointer_t<decltype(&szs_levenshtein_distances_init)>;
+    using init_weighted_t = std::remove_pointer_t<decltype(&szs_needleman_wunsch_scores_init)>;
+    using call_distances_t = std::remove_pointer_t<decltype(&szs_levenshtein_distances_u64tape)>;
+    using call_scores_t = std::remove_pointer_t<decltype(&szs_needleman_wunsch_scores_u64tape)>;
+    using free_t = std::remove_pointer_t<decltype(&szs_levenshtein_distances_free)>;
+    static_assert(std::is_same_v<init_levenshtein_t, std::remove_pointer_t<decltype(&szs_levenshtein_distances_utf8_init)>>);
+    static_assert(std::is_same_v<init_weighted_t, std::remove_pointer_t<decltype(&szs_smith_waterman_scores_init)>>);
+    static_assert(std::is_same_v<call_distances_t, std::remove_pointer_t<decltype(&szs_levenshtein_distances_utf8_u64tape)>>);
+    static_assert(std::is_same_v<call_scores_t, std::remove_pointer_t<decltype(&szs_smith_waterman_scores_u64tape)>>);
 
-    sz_capability_t (*capabilities)() = nullptr;
-    sz_status_t (*scope_cpu)(sz_size_t, szs_device_scope_t *, char const **) = nullptr;
-    sz_status_t (*scope_gpu)(sz_size_t, szs_device_scope_t *, char const **) = nullptr;
-    void (*scope_free)(szs_device_scope_t) = nullptr;
+    decltype(&szs_capabilities) capabilities = nullptr;
+    decltype(&szs_device_scope_init_cpu_cores) scope_cpu = nullptr;
+    decltype(&szs_device_scope_init_gpu_device) scope_gpu = nullptr;
+    decltype(&szs_device_scope_free) scope_free = nullptr;
     init_levenshtein_t *levenshtein_init = nullptr, *levenshtein_utf8_init = nullptr;
     init_weighted_t *needleman_wunsch_init = nullptr, *smith_waterman_init = nullptr;
-    call_t *levenshtein = nullptr, *levenshtein_utf8 = nullptr, *needleman_wunsch = nullptr, *smith_waterman = nullptr;
+    call_distances_t *levenshtein = nullptr, *levenshtein_utf8 = nullptr;
+    call_scores_t *needleman_wunsch = nullptr, *smith_waterman = nullptr;
     free_t *levenshtein_free = nullptr, *levenshtein_utf8_free = nullptr, *needleman_wunsch_free = nullptr,
            *smith_waterman_free = nullptr;
-    sz_status_t (*last_call_stats)(void const *, szs_b200_call_stats_t *) = nullptr; // only this repo's library
+    decltype(&szs_b200_last_call_stats) last_call_stats = nullptr; // only this repo's library exports it
 
     szs_device_scope_t scope = nullptr;
     bool on_gpu = false;
@@ -98,23 +103,23 @@ struct Library {
     explicit Library(std::string const &library_path) : path(library_path) {
         handle = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!handle) throw std::runtime_error(std::string("dlopen failed: ") + dlerror());
-        capabilities = symbol<sz_capability_t()>("szs_capabilities");
-        scope_cpu = symbol<sz_status_t(sz_size_t, szs_device_scope_t *, char const **)>("szs_device_scope_init_cpu_cores");
-        scope_gpu = symbol<sz_status_t(sz_size_t, szs_device_scope_t *, char const **)>("szs_device_scope_init_gpu_device");
-        scope_free = symbol<void(szs_device_scope_t)>("szs_device_scope_free");
+        capabilities = symbol<std::remove_pointer_t<decltype(capabilities)>>("szs_capabilities");
+        scope_cpu = symbol<std::remove_pointer_t<decltype(scope_cpu)>>("szs_device_scope_init_cpu_cores");
+        scope_gpu = symbol<std::remove_pointer_t<decltype(scope_gpu)>>("szs_device_scope_init_gpu_device");
+        scope_free = symbol<std::remove_pointer_t<decltype(scope_free)>>("szs_device_scope_free");
         levenshtein_init = symbol<init_levenshtein_t>("szs_levenshtein_distances_init");
         levenshtein_utf8_init = symbol<init_levenshtein_t>("szs_levenshtein_distances_utf8_init");
         needleman_wunsch_init = symbol<init_weighted_t>("szs_needleman_wunsch_scores_init");
         smith_waterman_init = symbol<init_weighted_t>("szs_smith_waterman_scores_init");
-        levenshtein = symbol<call_t>("szs_levenshtein_distances_u64tape");
-        levenshtein_utf8 = symbol<call_t>("szs_levenshtein_distances_utf8_u64tape");
-        needleman_wunsch = symbol<call_t>("szs_needleman_wunsch_scores_u64tape");
-        smith_waterman = symbol<call_t>("szs_smith_waterman_scores_u64tape");
+        levenshtein = symbol<call_distances_t>("szs_levenshtein_distances_u64tape");
+        levenshtein_utf8 = symbol<call_distances_t>("szs_levenshtein_distances_utf8_u64tape");
+        needleman_wunsch = symbol<call_scores_t>("szs_needleman_wunsch_scores_u64tape");
+        smith_waterman = symbol<call_scores_t>("szs_smith_waterman_scores_u64tape");
         levenshtein_free = symbol<free_t>("szs_levenshtein_distances_free");
         levenshtein_utf8_free = symbol<free_t>("szs_levenshtein_distances_utf8_free");
         needleman_wunsch_free = symbol<free_t>("szs_needleman_wunsch_scores_free");
         smith_waterman_free = symbol<free_t>("szs_smith_waterman_scores_free");
-        last_call_stats = symbol<sz_status_t(void const *, szs_b200_call_stats_t *)>("szs_b200_last_call_stats", false);
+        last_call_stats = symbol<std::remove_pointer_t<decltype(last_call_stats)>>("szs_b200_last_call_stats", false);
     }
 
     /** GPU scope when the library reports CUDA capabilities and a device answers, else all CPU cores. */
@@ -290,13 +295,15 @@ struct Outcome {
     bool skipped = true;
     double seconds = 0, cells = 0, bytes = 0, kernel_milliseconds = 0, kernel_cells = 0;
     std::size_t calls = 0, pairs = 0, stress_calls = 0, errors = 0;
+    std::int64_t last_tile_min = 0, last_tile_max = 0; // extremes of the last scored tile: a sanity line in the log
 };
 
 struct Runner {
     Library &library;
     Corpus const &corpus;
     Shape shape;
-    Library::call_t *call = nullptr;
+    Library::call_distances_t *call_distances = nullptr; // exactly one of the two is set
+    Library::call_scores_t *call_scores = nullptr;
     Library::free_t *release = nullptr;
     void *engine = nullptr;
     std::uint64_t seed = 42;
@@ -339,7 +346,9 @@ struct Runner {
 
         auto invoke = [&](sz_sequence_u64tape_t q, sz_sequence_u64tape_t c, std::int64_t *out, std::size_t stride) {
             char const *why = nullptr;
-            sz_status_t const status = call(engine, library.scope, &q, &c, out, stride, &why);
+            sz_status_t const status =
+                call_distances ? call_distances(engine, library.scope, &q, &c, reinterpret_cast<sz_size_t *>(out), stride, &why)
+                               : call_scores(engine, library.scope, &q, &c, reinterpret_cast<sz_ssize_t *>(out), stride, &why);
             if (status != sz_success_k)
                 throw std::runtime_error(outcome.name + " failed with status " + std::to_string(status) + ": " +
                                          (why ? why : ""));
@@ -370,6 +379,8 @@ struct Runner {
             }
         outcome.pairs += shape.scored_pairs();
         outcome.calls += 1;
+        auto const extremes = std::minmax_element(results.begin(), results.end());
+        outcome.last_tile_min = *extremes.first, outcome.last_tile_max = *extremes.second;
     }
 };
 
@@ -394,6 +405,8 @@ void print_outcome(Outcome const &outcome, Outcome const *against) {
                 per_call * 1e3, outcome.calls, outcome.pairs);
     std::printf("> Efficiency: %.2f GOps/s (cell updates per second, wall clock through the C ABI)\n",
                 outcome.cells / outcome.seconds / 1e9);
+    std::printf("> Results of the last tile: min %lld, max %lld\n", static_cast<long long>(outcome.last_tile_min),
+                static_cast<long long>(outcome.last_tile_max));
     if (outcome.kernel_milliseconds > 0)
         std::printf("> Kernel: %.2f GCUPS @ %.3f ms device-measured (excludes host materialization)\n",
                     outcome.kernel_cells / (outcome.kernel_milliseconds * 1e6), outcome.kernel_milliseconds);
@@ -478,7 +491,7 @@ void bench_levenshtein(Settings const &settings, Corpus const &corpus, std::vect
                                                     library.engine_capabilities(), &runner.engine, &why);
                     if (status != sz_success_k)
                         throw std::runtime_error(std::string("engine construction failed: ") + (why ? why : "?"));
-                    runner.call = variant.utf8 ? library.levenshtein_utf8 : library.levenshtein;
+                    runner.call_distances = variant.utf8 ? library.levenshtein_utf8 : library.levenshtein;
                     runner.release = variant.utf8 ? library.levenshtein_utf8_free : library.levenshtein_free;
                 };
                 auto name_of = [&](Library const &library, bool is_baseline) {
@@ -523,11 +536,11 @@ void bench_needleman_wunsch_smith_waterman(Settings const &settings, Corpus cons
             auto prepare = [&](Library &library, Runner &runner) {
                 char const *why = nullptr;
                 auto init = variant.local ? library.smith_waterman_init : library.needleman_wunsch_init;
-                sz_status_t const status = init(table, byte_to_class, -4, variant.affine ? -1 : -4, nullptr,
+                sz_status_t const status = init(byte_to_class, table, -4, variant.affine ? -1 : -4, nullptr,
                                                 library.engine_capabilities(), &runner.engine, &why);
                 if (status != sz_success_k)
                     throw std::runtime_error(std::string("engine construction failed: ") + (why ? why : "?"));
-                runner.call = variant.local ? library.smith_waterman : library.needleman_wunsch;
+                runner.call_scores = variant.local ? library.smith_waterman : library.needleman_wunsch;
                 runner.release = variant.local ? library.smith_waterman_free : library.needleman_wunsch_free;
             };
             auto name_of = [&](Library const &library, bool is_baseline) {
