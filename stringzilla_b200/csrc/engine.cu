@@ -1572,6 +1572,12 @@ static sz_status_t init_weighted(szb::Algorithm algorithm, sz_u8_t const *byte_t
                                  sz_error_cost_t extend, void **engine, char const **error_message) {
     if (!byte_to_class || !class_substitution_costs)
         return szb::report(szb::fail(sz_status_unknown_k, "Substitution tables are null"), error_message);
+    // The reference indexes its 32x32 table with whatever the map holds (serial.hpp:196-203: out-of-range classes read
+    // past the table). Refuse them here instead: the profile builder would otherwise do the same on device memory.
+    for (int byte = 0; byte < 256; ++byte)
+        if (byte_to_class[byte] >= 32)
+            return szb::report(szb::fail(sz_unexpected_dimensions_k, "byte_to_class maps a byte to a class index above 31"),
+                               error_message);
     Engine *made = nullptr;
     sz_status_t status = make_engine(algorithm, engine, error_message, &made);
     if (status != sz_success_k) return status;

@@ -63,6 +63,12 @@ def test_engine_lifecycle_without_gpu(library_built):
         assert engine_type(byte_to_class, costs, open=-4, extend=-1)._handle
     with pytest.raises(ValueError):
         szb.NeedlemanWunschScores(byte_to_class, costs[:8], open=-4, extend=-1)
+    # A class index outside the 32x32 table (e.g. the two tables passed in each other's place) is refused at construction.
+    out_of_range = byte_to_class.copy()
+    out_of_range[ord("Q")] = 32
+    with pytest.raises(szb.SimilarityError) as refusal:
+        szb.SmithWatermanScores(out_of_range, costs, open=-4, extend=-1)
+    assert refusal.value.status_name == "unexpected_dimensions"
 
 
 def test_no_cpu_fallback(library_built):
