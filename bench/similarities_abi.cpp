@@ -23,6 +23,7 @@
  *      STRINGWARS_FILTER          regular expression over benchmark names
  *      STRINGWARS_BATCH           comma-separated query counts overriding the shape sweep
  *      STRINGWARS_BATCH_PER_CORE  pairs per core (GPU SM or CPU thread), default 256
+ *      SZS_CPU_CORES              threads of a CPU device scope, default 0 = all (the reference's pool busy-waits)
  *      STRINGWARS_SYNTHETIC_LENGTH  mean token length of the synthetic corpus, default 1024 (lengths U[0.94L, 1.06L])
  *
  *  Synthetic corpus: `ACGT` tokens for the Levenshtein benchmarks, 20-amino-acid tokens for NW/SW, the methodology of the
@@ -123,13 +124,13 @@ struct Library {
     }
 
     /** GPU scope when the library reports CUDA capabilities and a device answers, else all CPU cores. */
-    void open_scope() {
+    void open_scope(std::size_t cpu_cores) {
         char const *why = nullptr;
         if ((capabilities() & sz_cap_cuda_k) && scope_gpu(0, &scope, &why) == sz_success_k) {
             on_gpu = true;
             return;
         }
-        if (scope_cpu(0, &scope, &why) != sz_success_k)
+        if (scope_cpu(cpu_cores, &scope, &why) != sz_success_k)
             throw std::runtime_error(path + ": no usable device scope: " + (why ? why : "?"));
     }
 
@@ -585,12 +586,14 @@ int main(int, char const **argv) {
         settings.filter = env_or("STRINGWARS_FILTER", "");
 
         Library accelerated(env_or("SZS_ACCELERATED_LIB", root + "/stringzilla_b200/lib/libstringzillas_b200.so"));
-        accelerated.open_scope();
+        // The reference's CPU pool busy-waits between calls: on a host with a CPU quota below its core count, cap it.
+        std::size_t const cpu_cores = std::stoull(env_or("SZS_CPU_CORES", "0")); // 0 = every core the library sees
+        accelerated.open_scope(cpu_cores);
         std::string const baseline_path = env_or("SZS_BASELINE_LIB", root + "/oracle/_ref/libstringzillas_ref.so");
         Library *baseline = nullptr;
         if (baseline_path != "none" && std::ifstream(baseline_path).good()) {
             baseline = new Library(baseline_path);
-            baseline->open_scope();
+            baseline->open_scope(cpu_cores);
         }
 
         std::size_t cores = accelerated.on_gpu ? streaming_multiprocessors() : 0;
@@ -635,7 +638,9 @@ int main(int, char const **argv) {
             bench_needleman_wunsch_smith_waterman(settings, corpus, make_shapes(corpus, cores), accelerated, baseline);
         }
         std::printf("\nAll benchmarks finished.\n");
-        return 0;
+        std::fflush(stdout);
+        // Leave without static destructors: a CUDA runtime tearing down beside a still-spinning CPU pool can take minutes.
+        std::_Exit(0);
     }
     catch (std::exception const &error) {
         std::fprintf(stderr, "Failed with: %s\n", error.what());

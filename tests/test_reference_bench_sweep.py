@@ -21,9 +21,9 @@ REFERENCE = ROOT / "oracle" / "_ref" / "libstringzillas_ref.so"
 def run_benchmark(**overrides) -> str:
     subprocess.run(["make", "-C", str(ROOT / "bench")], check=True, capture_output=True)
     env = dict(os.environ, STRINGWARS_DURATION="0.02", STRINGWARS_STRESS="1", STRINGWARS_STRESS_DURATION="0",
-               STRINGWARS_BATCH_PER_CORE="1", STRINGWARS_SYNTHETIC_LENGTH="64")
+               STRINGWARS_BATCH_PER_CORE="1", STRINGWARS_SYNTHETIC_LENGTH="64", SZS_CPU_CORES="4")
     env.update(overrides)
-    done = subprocess.run([str(BINARY)], env=env, capture_output=True, text=True, timeout=900)
+    done = subprocess.run([str(BINARY)], env=env, capture_output=True, text=True, timeout=300)
     assert done.returncode == 0, done.stdout[-2000:] + done.stderr[-2000:]
     return done.stdout
 
