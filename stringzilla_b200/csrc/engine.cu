@@ -66,6 +66,16 @@ __global__ void byte_presence_kernel(uint8_t const *in, uint64_t n, uint32_t *fl
     if (threadIdx.x < 256 && seen[threadIdx.x]) flags[threadIdx.x] = 1;
 }
 
+/** Role-swapped calls score (candidate, query): `swapped` is (columns x rows), `home` becomes (rows x columns). */
+__global__ void transpose_results_kernel(int64_t const *swapped, int64_t *home, uint64_t rows, uint64_t columns) {
+    uint64_t const total = rows * columns;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t const row = idx / columns, column = idx % columns;
+        home[idx] = swapped[column * rows + row];
+    }
+}
+
 /** Symmetric mode: mirror the lower triangle (query i, candidate j < i) into the upper one (serial.hpp:3183-3184). */
 __global__ void mirror_lower_kernel(int64_t *results, uint64_t n, uint64_t stride) {
     uint64_t const total = n * n;
@@ -126,6 +136,7 @@ __global__ void utf8_decode_kernel(uint8_t const *bytes, uint32_t const *byte_of
  *  small CJK corpora), ranking them into byte ids turns the rune problem into a byte problem and unlocks every
  *  byte-level kernel, including the bit-parallel ones. An open-addressing table in global memory collects the runes.
  */
+constexpr size_t kRoleSwapRows = 32; ///< calls with fewer query rows than this (and more candidates) trade roles
 constexpr uint32_t kRuneTableSlots = 1u << 16;
 constexpr uint32_t kRuneEmpty = 0xFFFFFFFFu; // no rune: the unchecked decoder yields at most 21 bits
 
@@ -384,7 +395,7 @@ struct Engine {
 
     // Grow-only device state, one set per engine: engines are not re-entrant.
     StagedSet queries, candidates;
-    DeviceBuffer results, scoring, lut, flags, query_flags, rune_table, rune_ranks, rune_state, slots, jobs, order, counters, scratch, myers_candidates, positions;
+    DeviceBuffer results, results_home, scoring, lut, flags, query_flags, rune_table, rune_ranks, rune_state, slots, jobs, order, counters, scratch, myers_candidates, positions;
     PinnedBuffer upload, upload_model;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     // Independent launches of one call (different strip widths, word counts, families) overlap their tails on side
@@ -1140,36 +1151,50 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
 
     // 1. Stage both sides.
     if (Failure failure = stage_set(queries_view, engine.queries, stream, stats)) return failure;
-    StagedSet &qs = engine.queries;
+    StagedSet &caller_queries = engine.queries;
     if (!symmetric)
         if (Failure failure = stage_set(candidates_view, engine.candidates, stream, stats)) return failure;
-    StagedSet &cs = symmetric ? engine.queries : engine.candidates;
+    StagedSet &caller_candidates = symmetric ? engine.queries : engine.candidates;
 
-    size_t const n_queries = qs.count, n_candidates = cs.count;
-    if (whole_matrix) row_begin = 0, row_end = n_queries;
-    if (row_end > n_queries || row_begin > row_end) return fail(sz_unexpected_dimensions_k, "Row range out of bounds");
-    if (n_candidates && stride < n_candidates)
+    size_t const caller_rows = caller_queries.count, caller_columns = caller_candidates.count;
+    if (whole_matrix) row_begin = 0, row_end = caller_rows;
+    if (row_end > caller_rows || row_begin > row_end) return fail(sz_unexpected_dimensions_k, "Row range out of bounds");
+    if (caller_columns && stride < caller_columns)
         return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
-    size_t const n_rows = row_end - row_begin;
-    if (n_rows == 0 || n_candidates == 0) {
+    if (row_end == row_begin || caller_columns == 0) {
         SZB_CUDA(cudaStreamSynchronize(stream));
         engine.stats = stats;
         return ok();
     }
     if (!results) return fail(sz_unexpected_dimensions_k, "Results pointer is null");
-    if (n_queries >= 0xFFFFFFF0ull || n_candidates >= 0xFFFFFFF0ull)
+    if (caller_rows >= 0xFFFFFFF0ull || caller_columns >= 0xFFFFFFF0ull)
         return fail(sz_overflow_risk_k, "Too many strings for one call");
 
     trace.mark("staged");
     // 2. Which symbols are we scoring: byte presence for the Levenshtein alphabet, UTF-8 decoding / rune ranking.
     uint32_t present[256] = {0};
     bool wide_symbols = false;
-    if (Failure failure = resolve_symbols(engine, stream, symmetric, qs, cs, stats, present, wide_symbols)) return failure;
+    if (Failure failure = resolve_symbols(engine, stream, symmetric, caller_queries, caller_candidates, stats, present,
+                                          wide_symbols))
+        return failure;
     trace.mark("alphabet known");
     Model model;
     build_model(engine, present, wide_symbols, model);
-    if (!fits_s32(engine, (uint64_t)qs.longest + cs.longest))
+    if (!fits_s32(engine, (uint64_t)caller_queries.longest + caller_candidates.longest))
         return fail(sz_overflow_risk_k, "Pair too long for 32-bit DP cells");
+
+    // Retrieval-shaped calls (a handful of queries against many candidates) trade roles: a kernel keeps the *candidate*
+    // resident (match table / substitution profile) and streams 32 / G queries per warp sweep past it, so with fewer
+    // queries than that most of each warp idles and every candidate pays its set-up for one string. Every score on this
+    // path is symmetric under exchanging the two strings when the substitution costs are, so the few strings become the
+    // resident side, the many stream, and the (columns x rows) result is transposed on the way home.
+    bool const swapped = !symmetric && whole_matrix && model.symmetric_costs && caller_rows < kRoleSwapRows &&
+                         caller_rows < caller_columns;
+    StagedSet &qs = swapped ? caller_candidates : caller_queries;
+    StagedSet &cs = swapped ? caller_queries : caller_candidates;
+    size_t const n_queries = qs.count, n_candidates = cs.count;
+    if (swapped) row_begin = 0, row_end = n_queries;
+    size_t const n_rows = row_end - row_begin;
 
     SZB_CUDA(engine.scoring.reserve(sizeof(Scoring)));
     SZB_CUDA(engine.lut.reserve(256));
@@ -1269,6 +1294,9 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     }
     SZB_CUDA(cudaMemsetAsync(engine.counters.ptr, 0, (plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64, stream));
     SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
+    if (swapped) {
+        SZB_CUDA(engine.results_home.reserve(n_rows * n_candidates * sizeof(int64_t)));
+    }
     // Launches overlap on side streams: every plan gets its own per-CTA boundary scratch.
     if (scratch_words_per_cta)
         SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms * plans.size()));
@@ -1372,9 +1400,22 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
 
     trace.mark("kernels launched");
     // 9. Results home: a strided 2-D copy into the caller's matrix (host, pinned, managed or device memory).
-    SZB_CUDA(cudaMemcpy2DAsync((int64_t *)results + row_begin * stride, stride * sizeof(int64_t), engine.results.ptr,
-                               n_candidates * sizeof(int64_t), n_candidates * sizeof(int64_t), n_rows,
-                               cudaMemcpyDefault, stream));
+    if (swapped) {
+        uint64_t const total = (uint64_t)caller_rows * caller_columns;
+        int const blocks = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);
+        transpose_results_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(),
+                                                             engine.results_home.as<int64_t>(), caller_rows, caller_columns);
+        SZB_CUDA(cudaGetLastError());
+        stats.kernel_launches++;
+        SZB_CUDA(cudaMemcpy2DAsync(results, stride * sizeof(int64_t), engine.results_home.ptr,
+                                   caller_columns * sizeof(int64_t), caller_columns * sizeof(int64_t), caller_rows,
+                                   cudaMemcpyDefault, stream));
+    }
+    else {
+        SZB_CUDA(cudaMemcpy2DAsync((int64_t *)results + row_begin * stride, stride * sizeof(int64_t), engine.results.ptr,
+                                   n_candidates * sizeof(int64_t), n_candidates * sizeof(int64_t), n_rows,
+                                   cudaMemcpyDefault, stream));
+    }
     if (pointer_is_host_readable(results)) stats.d2h_bytes += n_rows * n_candidates * sizeof(int64_t);
     SZB_CUDA(cudaEventRecord(engine.events[3], stream));
     SZB_CUDA(cudaStreamSynchronize(stream));

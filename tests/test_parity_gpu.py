@@ -436,6 +436,43 @@ def test_arrow_arrays_as_inputs(scope):
     assert np.array_equal(utf8(pa.array(greek), None, scope), support.oracle_levenshtein_utf8([g.encode() for g in greek]))
 
 
+def test_retrieval_shapes_trade_roles(scope):
+    """A handful of queries against many candidates: with symmetric costs the engine keeps the queries resident and
+    streams the candidates (results transposed on the way home); asymmetric tables and row shards keep their roles."""
+    rng = np.random.default_rng(61)
+    byte_to_class, blosum = scoring.blosum62()
+    skewed = blosum.copy()
+    skewed[3, 7] += 2  # no longer symmetric: roles must stay
+    for n_queries, n_candidates, low, high in ((1, 700, 0, 300), (3, 257, 100, 1200), (31, 40, 0, 90), (2, 3, 2000, 5000)):
+        dna_q = support.random_strings(rng, n_queries, low, high, support.DNA)
+        dna_c = support.mutated_copies(rng, (dna_q * (n_candidates // n_queries + 1))[:n_candidates], 0.2, support.DNA)
+        for costs, kwargs in (((0, 1, 1, 1), {}), ((0, 1, 1, 1), {"bit_parallel": False}), ((1, 3, 3, 3), {}), ((1, 3, 4, 2), {})):
+            out = np.full((n_queries, n_candidates + 5), 77, dtype=np.uint64)  # a wider matrix: the stride is honoured
+            szb.LevenshteinDistances(*costs, **kwargs)(dna_q, dna_c, scope, out=out[:, :n_candidates])
+            assert np.array_equal(out[:, :n_candidates], support.oracle_levenshtein(dna_q, dna_c, *costs)), (n_queries, costs)
+            assert (out[:, n_candidates:] == 77).all()
+        prot_q = support.random_strings(rng, n_queries, min(low, 1000), min(high, 1500), support.PROTEIN)
+        prot_c = support.random_strings(rng, n_candidates, min(low, 1000), min(high, 1500), support.PROTEIN)
+        for table in (blosum, skewed):
+            for engine_type, local in ((szb.NeedlemanWunschScores, False), (szb.SmithWatermanScores, True)):
+                for gaps in ((-4, -4), (-4, -1)):
+                    got = engine_type(byte_to_class, table, open=gaps[0], extend=gaps[1])(prot_q, prot_c, scope)
+                    want = support.oracle_weighted(prot_q, prot_c, byte_to_class, table, gaps[0], gaps[1], local)
+                    assert np.array_equal(got, want), (n_queries, local, gaps, table is skewed)
+    greek = ["αβγδ" * 20, "δγβα" * 7]
+    many = ["".join(rng.choice(list("αβγδε"), size=int(n))) for n in rng.integers(0, 120, size=90)]
+    got = szb.LevenshteinDistancesUTF8()(greek, many, scope)
+    assert np.array_equal(got, support.oracle_levenshtein_utf8([g.encode() for g in greek], [m.encode() for m in many]))
+    # A row shard of a retrieval-shaped call keeps the ordinary roles and fills only its rows.
+    queries = support.random_strings(rng, 4, 50, 200, support.DNA)
+    candidates = support.random_strings(rng, 300, 50, 200, support.DNA)
+    out = np.zeros((4, 300), dtype=np.uint64)
+    engine = szb.LevenshteinDistances()
+    engine.score_rows(queries, candidates, 1, 3, device=scope, out=out)
+    want = support.oracle_levenshtein(queries, candidates)
+    assert np.array_equal(out[1:3], want[1:3]) and (out[0] == 0).all() and (out[3] == 0).all()
+
+
 def test_row_shards_reassemble_the_matrix(scope):
     rng = np.random.default_rng(23)
     queries = support.random_strings(rng, 13, 0, 200, support.DNA)
