@@ -319,11 +319,62 @@ SZS_B200_API sz_status_t szs_b200_debug_schedule(void const *engine, sz_u32_t co
 /** Score only query rows [row_begin, row_end) of the cross product; `results` still addresses the FULL matrix
  *  (`results[q * stride + c]`), rows outside the range are left untouched. This is the shard primitive of the
  *  multi-GPU partition: each rank owns a contiguous block of query rows balanced by total query length.
- *  `family`: 0 Levenshtein (results are sz_size_t), 1 Needleman-Wunsch, 2 Smith-Waterman (sz_ssize_t). */
+ *  `family`: 0 Levenshtein (results are sz_size_t), 1 Needleman-Wunsch, 2 Smith-Waterman (sz_ssize_t).
+ *  With `candidates == NULL` (symmetric self-similarity) a row shard scores the cells (query i, candidate j) of its rows
+ *  for j < row_end only — the reference's orientation of the lower triangle (serial.hpp:3171-3185) — and the caller
+ *  mirrors the upper triangle once every shard is in (the multi-GPU entries below do). */
 SZS_B200_API sz_status_t szs_b200_scores_u64tape_rows(int family, void *engine, szs_device_scope_t device,
                                                       sz_sequence_u64tape_t const *queries,
                                                       sz_sequence_u64tape_t const *candidates, sz_size_t row_begin,
                                                       sz_size_t row_end, void *results,
+                                                      sz_size_t results_row_stride, char const **error_message);
+
+/* ---- Multi-GPU (the reference has none: `szs_device_scope_init_gpu_device` takes ONE device id,
+ *      stringzillas.h:137-138, and no NCCL/MPI/peer-copy symbol exists in its tree) ------------------------------- */
+
+/** Contiguous blocks of query rows of near-equal cost, the partition every multi-GPU entry below uses: a row costs
+ *  `len(q) * sum(len(c))`; in a symmetric call (`symmetric != 0`) row i costs `len(i) * sum(len(j), j <= i)`.
+ *  Writes `parts + 1` bounds into `bounds`; host-only, no GPU needed. */
+SZS_B200_API sz_status_t szs_b200_partition_rows(sz_u64_t const *lengths, sz_size_t count, sz_size_t parts, int symmetric,
+                                                 sz_u64_t *bounds);
+
+/** (1) ONE process driving several GPUs: a device group owns one scope (device + stream) and one parked host thread per
+ *  GPU; `gpu_devices == NULL` takes every visible device. The reference already allows different scopes on different
+ *  host threads (types.cuh:433-444); this is the orchestrator on top of that contract. */
+typedef void *szs_b200_device_group_t;
+SZS_B200_API sz_status_t szs_b200_device_group_init(sz_size_t const *gpu_devices, sz_size_t count,
+                                                    szs_b200_device_group_t *group, char const **error_message);
+SZS_B200_API sz_status_t szs_b200_device_group_size(szs_b200_device_group_t group, sz_size_t *count);
+SZS_B200_API void szs_b200_device_group_free(szs_b200_device_group_t group);
+
+/** The `*_u64tape` call of `family` (0 Levenshtein, 1 Needleman-Wunsch, 2 Smith-Waterman) sharded by query rows over
+ *  the group's GPUs. Every shard reads the inputs straight from the caller's memory (each GPU over its own PCIe link)
+ *  and writes its rows straight into the caller's matrix: no collective is involved. `engine` is an ordinary engine
+ *  handle; per-device clones of it are kept inside. `candidates == NULL` requests symmetric self-similarity. */
+SZS_B200_API sz_status_t szs_b200_scores_u64tape_sharded(int family, void *engine, szs_b200_device_group_t group,
+                                                         sz_sequence_u64tape_t const *queries,
+                                                         sz_sequence_u64tape_t const *candidates, void *results,
+                                                         sz_size_t results_row_stride, char const **error_message);
+
+/** (2) ONE process per GPU (e.g. under `torch.distributed.run`): a communicator wraps an NCCL communicator over the
+ *  ranks' GPUs. NCCL is resolved at run time (the copy already in the process, `SZS_B200_NCCL_LIBRARY`, or
+ *  libnccl.so.2), so the library loads and scores on one GPU without it. Rank 0 creates the 128-byte identifier and
+ *  hands it to the other ranks by any out-of-band means; every rank then calls `szs_b200_comm_init`. */
+#define SZS_B200_COMM_ID_BYTES 128
+typedef void *szs_b200_comm_t;
+SZS_B200_API sz_status_t szs_b200_comm_unique_id(void *unique_id, char const **error_message);
+SZS_B200_API sz_status_t szs_b200_comm_init(void const *unique_id, int world_size, int rank, sz_size_t gpu_device,
+                                            szs_b200_comm_t *comm, char const **error_message);
+SZS_B200_API void szs_b200_comm_free(szs_b200_comm_t comm);
+
+/** Collective call, entered by every rank with its own engine and GPU scope. Rank 0 passes the tapes (host, pinned,
+ *  managed or device memory) and the result matrix; the other ranks pass NULL for all three. ONE NCCL broadcast of the
+ *  packed inputs (after a 64-byte header), row-sharded scoring, ONE grouped send/recv gather of the int64 score slabs
+ *  to rank 0, which copies the whole matrix into `results`. Every (query, candidate) pair is independent, so nothing
+ *  crosses GPUs during the DP itself. */
+SZS_B200_API sz_status_t szs_b200_comm_scores_u64tape(int family, void *engine, szs_device_scope_t device,
+                                                      szs_b200_comm_t comm, sz_sequence_u64tape_t const *queries,
+                                                      sz_sequence_u64tape_t const *candidates, void *results,
                                                       sz_size_t results_row_stride, char const **error_message);
 
 #ifdef __cplusplus

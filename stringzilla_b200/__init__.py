@@ -18,6 +18,8 @@ from . import _abi
 from ._abi import CallStats, SimilarityError  # noqa: F401  (re-exported)
 
 __all__ = [
+    "Communicator",
+    "DeviceGroup",
     "DeviceScope",
     "LevenshteinDistances",
     "LevenshteinDistancesUTF8",
@@ -154,6 +156,68 @@ class DeviceScope:
             self._lib.szs_device_scope_free(handle)
 
 
+class DeviceGroup:
+    """Several GPUs of one box driven from THIS process (`szs_b200_device_group_*`): one scope and one parked host
+    thread per GPU. `gpu_devices=None` takes every visible device. A B200 addition — the reference has no multi-GPU."""
+
+    def __init__(self, gpu_devices: "SequenceType[int] | None" = None, library_path=None):
+        self._lib = _library(library_path)
+        self._handle = ct.c_void_p()
+        message = ct.c_char_p()
+        if gpu_devices is None:
+            status = self._lib.szs_b200_device_group_init(None, 0, ct.byref(self._handle), ct.byref(message))
+        else:
+            ids = (ct.c_uint64 * len(gpu_devices))(*[int(d) for d in gpu_devices])
+            status = self._lib.szs_b200_device_group_init(ids, len(gpu_devices), ct.byref(self._handle), ct.byref(message))
+        _abi.check(status, message)
+
+    @property
+    def handle(self) -> ct.c_void_p:
+        return self._handle
+
+    def __len__(self) -> int:
+        count = ct.c_uint64()
+        self._lib.szs_b200_device_group_size(self._handle, ct.byref(count))
+        return int(count.value)
+
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            self._lib.szs_b200_device_group_free(handle)
+
+
+class Communicator:
+    """One rank of a one-process-per-GPU job (`szs_b200_comm_*`): wraps an NCCL communicator created from C. Rank 0
+    draws `Communicator.unique_id()` and passes the 128 bytes to the other ranks out of band (e.g. a
+    `torch.distributed` broadcast or a file)."""
+
+    def __init__(self, unique_id: bytes, world_size: int, rank: int, gpu_device: int, library_path=None):
+        if len(unique_id) != _abi.COMM_ID_BYTES:
+            raise ValueError(f"unique_id must be {_abi.COMM_ID_BYTES} bytes")
+        self._lib = _library(library_path)
+        self._handle = ct.c_void_p()
+        self.world_size, self.rank = int(world_size), int(rank)
+        message = ct.c_char_p()
+        buffer = ct.create_string_buffer(bytes(unique_id), _abi.COMM_ID_BYTES)
+        _abi.check(self._lib.szs_b200_comm_init(buffer, self.world_size, self.rank, int(gpu_device), ct.byref(self._handle),
+                                                ct.byref(message)), message)  # fmt: skip
+
+    @staticmethod
+    def unique_id(library_path=None) -> bytes:
+        buffer, message = ct.create_string_buffer(_abi.COMM_ID_BYTES), ct.c_char_p()
+        _abi.check(_library(library_path).szs_b200_comm_unique_id(buffer, ct.byref(message)), message)
+        return buffer.raw
+
+    @property
+    def handle(self) -> ct.c_void_p:
+        return self._handle
+
+    def __del__(self):
+        handle, self._handle = getattr(self, "_handle", None), None
+        if handle:
+            self._lib.szs_b200_comm_free(handle)
+
+
 def _resolve_capabilities(value, lib) -> int:
     if value is None:
         return int(lib.szs_capabilities())
@@ -210,6 +274,50 @@ class _Engine:
         """Shard primitive: fills only rows [row_begin, row_end) of the full-shape matrix `out`."""
         return self._call(queries, candidates, device, out, rows=(row_begin, row_end))
 
+    def sharded(self, queries, candidates=None, group: "DeviceGroup | None" = None, out: np.ndarray | None = None):
+        """The same cross product row-sharded over the GPUs of `group` from this process
+        (`szs_b200_scores_u64tape_sharded`): no collective, every GPU reads the inputs and writes its rows itself."""
+        queries = queries if isinstance(queries, Tape) else Tape(queries)
+        if candidates is not None and not isinstance(candidates, Tape):
+            candidates = Tape(candidates)
+        n_rows, n_cols = len(queries), len(candidates) if candidates is not None else len(queries)
+        if out is None:
+            out = np.zeros((n_rows, n_cols), dtype=self._result_dtype)
+        elif out.shape != (n_rows, n_cols) or out.dtype != self._result_dtype or out.strides[1] != out.itemsize:
+            raise ValueError("`out` must be a (queries x candidates) matrix of the engine's dtype with unit column stride")
+        stride = out.strides[0] // out.itemsize if n_rows > 1 else max(n_cols, 1)
+        message = ct.c_char_p()
+        status = self._lib.szs_b200_scores_u64tape_sharded(
+            self._family_index, self._handle, group.handle, queries.pointer(),
+            candidates.pointer() if candidates is not None else None, out.ctypes.data_as(ct.c_void_p), stride,
+            ct.byref(message))  # fmt: skip
+        _abi.check(status, message)
+        return out
+
+    def communicate(self, communicator: "Communicator", device: DeviceScope, queries=None, candidates=None,
+                    out: np.ndarray | None = None):
+        """Collective over a `Communicator` (`szs_b200_comm_scores_u64tape`): rank 0 passes the strings and receives the
+        whole matrix; the other ranks pass nothing and return None."""
+        message = ct.c_char_p()
+        if communicator.rank == 0:
+            queries = queries if isinstance(queries, Tape) else Tape(queries)
+            if candidates is not None and not isinstance(candidates, Tape):
+                candidates = Tape(candidates)
+            n_rows, n_cols = len(queries), len(candidates) if candidates is not None else len(queries)
+            if out is None:
+                out = np.zeros((n_rows, n_cols), dtype=self._result_dtype)
+            stride = out.strides[0] // out.itemsize if n_rows > 1 else max(n_cols, 1)
+            status = self._lib.szs_b200_comm_scores_u64tape(
+                self._family_index, self._handle, device.handle, communicator.handle, queries.pointer(),
+                candidates.pointer() if candidates is not None else None, out.ctypes.data_as(ct.c_void_p), stride,
+                ct.byref(message))  # fmt: skip
+        else:
+            out = None
+            status = self._lib.szs_b200_comm_scores_u64tape(self._family_index, self._handle, device.handle,
+                                                            communicator.handle, None, None, None, 0, ct.byref(message))
+        _abi.check(status, message)
+        return out
+
     @property
     def last_call_stats(self) -> CallStats:
         stats = CallStats()
@@ -249,6 +357,7 @@ class LevenshteinDistancesUTF8(_Engine):
     (python/stringzillas/similarities.c:519-547): edit distance over UTF-8 runes instead of bytes."""
 
     _family = "levenshtein_distances_utf8"
+    _family_index = 0  # a Levenshtein engine as far as the shard primitives are concerned
     _result_dtype = np.uint64
 
     def __init__(self, match: int = 0, mismatch: int = 1, open: int = 1, extend: int = 1, capabilities=None,

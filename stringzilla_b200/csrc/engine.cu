@@ -18,7 +18,9 @@
 #include "myers.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,7 +29,11 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 namespace szb {
 
@@ -350,24 +356,38 @@ struct InputView {
     }
 };
 
-static bool pointer_is_host_readable(void const *pointer) {
-    if (!pointer) return true;
+enum class MemoryKind { kPageable, kPinned, kManaged, kDevice };
+
+static MemoryKind memory_kind(void const *pointer) {
+    if (!pointer) return MemoryKind::kPageable;
     cudaPointerAttributes attributes;
     if (cudaPointerGetAttributes(&attributes, pointer) != cudaSuccess) {
         cudaGetLastError();
-        return true;
+        return MemoryKind::kPageable;
     }
-    return attributes.type != cudaMemoryTypeDevice;
+    switch (attributes.type) {
+    case cudaMemoryTypeHost: return MemoryKind::kPinned;
+    case cudaMemoryTypeManaged: return MemoryKind::kManaged;
+    case cudaMemoryTypeDevice: return MemoryKind::kDevice;
+    default: return MemoryKind::kPageable;
+    }
 }
 
-/** One side of the cross product, staged on the device. */
+static bool pointer_is_host_readable(void const *pointer) { return memory_kind(pointer) != MemoryKind::kDevice; }
+
+/** One side of the cross product: what the host knows about it, and where its bytes live on the device. */
 struct StagedSet {
     size_t count = 0;
     uint64_t total_bytes = 0;
-    std::vector<uint32_t> offsets; // count + 1, relative to the staged blob
+    std::vector<uint32_t> offsets; // count + 1, relative to the first byte of the collection
     uint32_t longest = 0;
+    // Where the caller keeps the bytes.
+    uint8_t const *blob = nullptr;           // tapes: first byte of the collection
+    sz_sequence_t const *sequence = nullptr; // callback sequences
+    bool host_readable = true;               // the bytes can be read by host code (pageable, pinned or managed memory)
+    uint8_t const *host_view = nullptr;      // the bytes as one host-readable run, when there is one
+    bool uploaded = false;                   // the raw bytes are in `raw`
     DeviceBuffer raw, classes, device_offsets;
-    uint8_t const *host_view = nullptr; // the staged bytes as the host can read them (nullptr for device-only input)
     DeviceBuffer rune_counts, rune_offsets, runes; // UTF-8 engines: the decoded symbol streams
     std::vector<uint32_t> rune_counts_host;
     PinnedBuffer gather; // only for callback sequences
@@ -375,6 +395,15 @@ struct StagedSet {
     void release() {
         raw.release(), classes.release(), device_offsets.release(), rune_counts.release(), rune_offsets.release();
         runes.release(), gather.release();
+    }
+    /** Calls `visit(pointer, length, index)` for every string; only valid when `host_readable`. */
+    template <typename visitor_type>
+    void for_each_host_string(visitor_type &&visit) const {
+        for (size_t i = 0; i < count; ++i) {
+            size_t const length = offsets[i + 1] - offsets[i];
+            uint8_t const *start = sequence ? (uint8_t const *)sequence->get_start(sequence->handle, i) : blob + offsets[i];
+            visit(start, length, i);
+        }
     }
 };
 
@@ -395,8 +424,12 @@ struct Engine {
 
     // Grow-only device state, one set per engine: engines are not re-entrant.
     StagedSet queries, candidates;
-    DeviceBuffer results, results_home, scoring, lut, flags, query_flags, rune_table, rune_ranks, rune_state, slots, jobs, order, counters, scratch, myers_candidates, positions;
-    PinnedBuffer upload, upload_model;
+    DeviceBuffer results, results_home, flags, query_flags, rune_table, rune_ranks, rune_state, scratch;
+    // Everything the host generates for one call (offsets, scoring model, class map, query order, slots, jobs,
+    // bit-parallel candidates, zeroed counters — and, for small host-resident inputs, the class-mapped strings
+    // themselves) travels in ONE pinned arena and ONE host-to-device copy.
+    PinnedBuffer arena_host, download;
+    DeviceBuffer arena_device;
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     // Independent launches of one call (different strip widths, word counts, families) overlap their tails on side
     // streams forked from, and joined back into, the scope's stream.
@@ -406,8 +439,11 @@ struct Engine {
     int events_device = -1;
     szs_b200_call_stats_t stats = {};
     std::mutex mutex;
+    // Multi-GPU calls (szs_b200_scores_u64tape_sharded) keep one clone of this engine per extra device.
+    std::vector<std::unique_ptr<Engine>> shards;
 
     ~Engine() {
+        if (events_device >= 0) cudaSetDevice(events_device);
         for (cudaEvent_t event : events)
             if (event) cudaEventDestroy(event);
         for (cudaEvent_t event : join_events)
@@ -416,25 +452,37 @@ struct Engine {
         for (cudaStream_t stream : side_streams)
             if (stream) cudaStreamDestroy(stream);
     }
+    /** A fresh engine with the same algorithm and costs (and no device state). */
+    std::unique_ptr<Engine> clone() const {
+        std::unique_ptr<Engine> copy(new (std::nothrow) Engine());
+        if (!copy) return copy;
+        copy->algorithm = algorithm, copy->match = match, copy->mismatch = mismatch, copy->open = open;
+        copy->extend = extend, copy->bit_parallel = bit_parallel, copy->utf8 = utf8;
+        std::memcpy(copy->byte_to_class, byte_to_class, sizeof(byte_to_class));
+        std::memcpy(copy->costs, costs, sizeof(costs));
+        return copy;
+    }
 };
 
 #pragma endregion
 
 #pragma region Staging
 
-/** Copies one collection to the device: raw bytes + offsets. Accepts host, pinned, managed or device memory. */
-static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, szs_b200_call_stats_t &stats) {
+/**
+ *  Reads the layout of one collection on the host: string count, 32-bit offsets relative to its first byte, the
+ *  longest string, and where the bytes are. Copies nothing but (for device-resident tapes) the offsets.
+ */
+static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) {
     size_t const count = view.count();
     set.count = count;
     set.offsets.resize(count + 1);
-    set.longest = 0;
-    uint8_t const *blob = nullptr;
-    bool contiguous = true;
-    set.host_view = nullptr;
+    set.longest = 0, set.blob = nullptr, set.sequence = nullptr, set.host_view = nullptr, set.uploaded = false;
+    set.host_readable = true;
 
     if (view.layout == InputView::kTape32 || view.layout == InputView::kTape64) {
         void const *offsets_pointer;
         size_t offset_width;
+        uint8_t const *blob;
         if (view.layout == InputView::kTape32) {
             auto const *tape = static_cast<sz_sequence_u32tape_t const *>(view.object);
             blob = (uint8_t const *)tape->data, offsets_pointer = tape->offsets, offset_width = 4;
@@ -443,9 +491,7 @@ static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, sz
             auto const *tape = static_cast<sz_sequence_u64tape_t const *>(view.object);
             blob = (uint8_t const *)tape->data, offsets_pointer = tape->offsets, offset_width = 8;
         }
-        if (count == 0) {
-            set.offsets[0] = 0, set.total_bytes = 0;
-        }
+        if (count == 0) { set.offsets[0] = 0, set.total_bytes = 0; }
         else {
             if (!offsets_pointer) return fail(sz_unexpected_dimensions_k, "Tape offsets are null");
             // Offsets are read on the host (as the reference does, cuda.cuh:4285-4295); bounce device-only ones.
@@ -457,83 +503,89 @@ static Failure stage_set(InputView view, StagedSet &set, cudaStream_t stream, sz
                 SZB_CUDA(cudaStreamSynchronize(stream));
                 host_offsets = set.offsets_bounce.data();
             }
-            uint64_t first, last;
-            if (offset_width == 4) {
-                auto const *o = static_cast<uint32_t const *>(host_offsets);
-                first = o[0], last = o[count];
-                if (last < first || last - first > 0xFFFFFFF0ull)
-                    return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
-                for (size_t i = 0; i <= count; ++i) set.offsets[i] = o[i] - (uint32_t)first;
+            // Every offset is validated as a 64-bit value before it is narrowed: monotone, and within 4 GB of the first.
+            uint64_t first, previous;
+            auto read = [&](size_t i) -> uint64_t {
+                return offset_width == 4 ? (uint64_t) static_cast<uint32_t const *>(host_offsets)[i]
+                                         : static_cast<uint64_t const *>(host_offsets)[i];
+            };
+            first = previous = read(0);
+            set.offsets[0] = 0;
+            for (size_t i = 1; i <= count; ++i) {
+                uint64_t const current = read(i);
+                if (current < previous) return fail(sz_unexpected_dimensions_k, "Tape offsets decrease");
+                if (current - first > 0xFFFFFFF0ull) return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
+                set.offsets[i] = (uint32_t)(current - first);
+                set.longest = std::max(set.longest, (uint32_t)(current - previous));
+                previous = current;
             }
-            else {
-                auto const *o = static_cast<uint64_t const *>(host_offsets);
-                first = o[0], last = o[count];
-                if (last < first || last - first > 0xFFFFFFF0ull)
-                    return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
-                for (size_t i = 0; i <= count; ++i) set.offsets[i] = (uint32_t)(o[i] - first);
-            }
-            set.total_bytes = last - first;
+            set.total_bytes = previous - first;
             blob += first;
         }
+        set.blob = blob;
+        set.host_readable = set.total_bytes == 0 || pointer_is_host_readable(blob);
+        if (set.host_readable) set.host_view = blob;
     }
     else {
         auto const *sequence = static_cast<sz_sequence_t const *>(view.object);
-        contiguous = false;
+        set.sequence = sequence;
         uint64_t running = 0;
         for (size_t i = 0; i < count; ++i) {
             set.offsets[i] = (uint32_t)running;
-            running += sequence->get_length(sequence->handle, i);
+            uint64_t const length = sequence->get_length(sequence->handle, i);
+            running += length;
             if (running > 0xFFFFFFF0ull) return fail(sz_overflow_risk_k, "Collection exceeds 4 GB of text");
+            set.longest = std::max(set.longest, (uint32_t)length);
         }
         set.offsets[count] = (uint32_t)running;
         set.total_bytes = running;
+        // Like the reference (cuda.cuh:4268-4272), only the first string's pointer is inspected.
+        set.host_readable = count == 0 || running == 0 || pointer_is_host_readable(sequence->get_start(sequence->handle, 0));
     }
-    for (size_t i = 0; i < count; ++i) {
-        if (set.offsets[i + 1] < set.offsets[i]) return fail(sz_unexpected_dimensions_k, "Tape offsets decrease");
-        set.longest = std::max(set.longest, set.offsets[i + 1] - set.offsets[i]);
-    }
+    return ok();
+}
 
+/** Copies the raw bytes of one collection to the device (`set.raw`). Accepts host, pinned, managed or device memory. */
+static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_stats_t &stats) {
     // Padding keeps the 16-byte vector loads of the class-mapping kernel in bounds.
     SZB_CUDA(set.raw.reserve(set.total_bytes + 256));
     SZB_CUDA(set.classes.reserve(set.total_bytes + 256));
-    SZB_CUDA(set.device_offsets.reserve((count + 1) * sizeof(uint32_t)));
-    if (set.total_bytes) {
-        if (contiguous) {
-            SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, blob, set.total_bytes, cudaMemcpyDefault, stream));
-            if (pointer_is_host_readable(blob)) stats.h2d_bytes += set.total_bytes, set.host_view = blob;
-        }
-        else {
-            auto const *sequence = static_cast<sz_sequence_t const *>(view.object);
-            sz_cptr_t const first = sequence->get_start(sequence->handle, 0);
-            if (pointer_is_host_readable(first)) {
-                SZB_CUDA(set.gather.reserve(set.total_bytes));
-                for (size_t i = 0; i < count; ++i) {
-                    size_t const length = set.offsets[i + 1] - set.offsets[i];
-                    if (length)
-                        std::memcpy((char *)set.gather.ptr + set.offsets[i], sequence->get_start(sequence->handle, i),
-                                    length);
-                }
-                SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, set.gather.ptr, set.total_bytes, cudaMemcpyHostToDevice,
-                                         stream));
-                stats.h2d_bytes += set.total_bytes;
-                set.host_view = (uint8_t const *)set.gather.ptr;
-            }
-            else {
-                for (size_t i = 0; i < count; ++i) {
-                    size_t const length = set.offsets[i + 1] - set.offsets[i];
-                    if (length)
-                        SZB_CUDA(cudaMemcpyAsync((char *)set.raw.ptr + set.offsets[i],
-                                                 sequence->get_start(sequence->handle, i), length, cudaMemcpyDefault,
-                                                 stream));
-                }
-            }
-        }
+    set.uploaded = true;
+    if (!set.total_bytes) return ok();
+    if (!set.sequence) {
+        SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, set.blob, set.total_bytes, cudaMemcpyDefault, stream));
+        if (set.host_readable) stats.h2d_bytes += set.total_bytes;
+        return ok();
     }
-    SZB_CUDA(cudaMemcpyAsync(set.device_offsets.ptr, set.offsets.data(), (count + 1) * sizeof(uint32_t),
-                             cudaMemcpyHostToDevice, stream));
-    stats.h2d_bytes += (count + 1) * sizeof(uint32_t);
+    sz_sequence_t const *sequence = set.sequence;
+    if (set.host_readable) {
+        SZB_CUDA(set.gather.reserve(set.total_bytes));
+        set.for_each_host_string([&](uint8_t const *start, size_t length, size_t i) {
+            if (length) std::memcpy((char *)set.gather.ptr + set.offsets[i], start, length);
+        });
+        SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, set.gather.ptr, set.total_bytes, cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += set.total_bytes;
+        set.host_view = (uint8_t const *)set.gather.ptr;
+        return ok();
+    }
+    for (size_t i = 0; i < set.count; ++i) {
+        size_t const length = set.offsets[i + 1] - set.offsets[i];
+        if (length)
+            SZB_CUDA(cudaMemcpyAsync((char *)set.raw.ptr + set.offsets[i], sequence->get_start(sequence->handle, i),
+                                     length, cudaMemcpyDefault, stream));
+    }
     return ok();
 }
+
+/** The per-call arena: sections are carved first (sizes only), then both copies are reserved once, then filled. */
+struct ArenaLayout {
+    size_t used = 0;
+    size_t carve(size_t bytes) {
+        size_t const at = used;
+        used = (used + bytes + 255) & ~(size_t)255;
+        return at;
+    }
+};
 
 #pragma endregion
 
@@ -670,11 +722,11 @@ static Failure ensure_events(Engine &engine, int device) {
         // The engine moves to another GPU (a scope of a different device): its grow-only buffers live on the old one.
         cudaSetDevice(engine.events_device);
         engine.queries.release(), engine.candidates.release();
-        for (DeviceBuffer *buffer : {&engine.results, &engine.scoring, &engine.lut, &engine.flags, &engine.query_flags,
-                                     &engine.rune_table, &engine.rune_ranks, &engine.rune_state, &engine.slots, &engine.jobs, &engine.order, &engine.counters, &engine.scratch,
-                                     &engine.myers_candidates, &engine.positions})
+        for (DeviceBuffer *buffer : {&engine.results, &engine.results_home, &engine.flags, &engine.query_flags,
+                                     &engine.rune_table, &engine.rune_ranks, &engine.rune_state, &engine.scratch,
+                                     &engine.arena_device})
             buffer->release();
-        engine.upload.release(), engine.upload_model.release();
+        engine.arena_host.release(), engine.download.release();
         cudaSetDevice(device);
     }
     for (cudaEvent_t &event : engine.events) {
@@ -693,10 +745,11 @@ static Failure ensure_events(Engine &engine, int device) {
     return ok();
 }
 
-/**
- *  @brief Scores query rows [row_begin, row_end) against every candidate and writes `results[q * stride + c]`.
- *         `candidates.object == nullptr` requests the symmetric self-similarity of the queries.
- */
+/** Grid of a grid-stride helper kernel: enough blocks for `items`, capped at a few waves of the device. */
+static int helper_grid(uint64_t items, int per_block, int device_sms, int waves) {
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>((items + per_block - 1) / per_block, (uint64_t)device_sms * waves));
+}
+
 /**
  *  @brief Steps 2-2b of a call: which symbols are we scoring?
  *
@@ -704,36 +757,48 @@ static Failure ensure_events(Engine &engine, int device) {
  *  into classes. UTF-8 engines additionally decide between three representations: pure ASCII stays bytes; at most 256
  *  distinct runes are ranked into byte ids (the staged byte streams and offsets are REPLACED by the id streams);
  *  anything else becomes UTF-32 symbol streams (`wide_symbols`), with offsets and lengths counted in symbols.
+ *
+ *  `packed` (small host-resident inputs: nothing has been uploaded yet, the host scans the caller's memory) is given up
+ *  here when a UTF-8 engine meets non-ASCII input: the rune machinery lives on the device.
  */
-static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetric, StagedSet &qs, StagedSet &cs,
-                               szs_b200_call_stats_t &stats, uint32_t (&present)[256], bool &wide_symbols) {
+static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetric, bool &packed, int device_sms,
+                               StagedSet &qs, StagedSet &cs, szs_b200_call_stats_t &stats, uint32_t (&present)[256],
+                               bool &wide_symbols) {
     // 2. The scoring model; Levenshtein compacts the alphabet of the candidates into <= 31 classes.
     if (engine.algorithm == Algorithm::kLevenshtein) {
         uint32_t query_present[256] = {0};
         bool const need_queries = engine.utf8 && !symmetric && qs.total_bytes;
         // Small host-resident inputs are scanned on the host: a kernel plus a D2H round-trip costs more than the scan.
         constexpr uint64_t host_scan_limit = 512 * 1024;
-        bool const scan_on_host = cs.total_bytes <= host_scan_limit && (cs.host_view || !cs.total_bytes) &&
-                                  (!need_queries || (qs.total_bytes <= host_scan_limit && qs.host_view));
-        if (scan_on_host) {
-            for (uint64_t i = 0; i < cs.total_bytes; ++i) present[cs.host_view[i]] = 1;
-            if (need_queries)
-                for (uint64_t i = 0; i < qs.total_bytes; ++i) query_present[qs.host_view[i]] = 1;
+        auto scannable = [&](StagedSet const &set) {
+            return !set.total_bytes || (set.total_bytes <= host_scan_limit && set.host_readable && (set.host_view || packed));
+        };
+        if (scannable(cs) && (!need_queries || scannable(qs))) {
+            auto scan = [](StagedSet const &set, uint32_t (&seen)[256]) {
+                if (set.host_view)
+                    for (uint64_t i = 0; i < set.total_bytes; ++i) seen[set.host_view[i]] = 1;
+                else
+                    set.for_each_host_string([&](uint8_t const *start, size_t length, size_t) {
+                        for (size_t i = 0; i < length; ++i) seen[start[i]] = 1;
+                    });
+            };
+            scan(cs, present);
+            if (need_queries) scan(qs, query_present);
         }
         else {
             SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
             SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
             if (cs.total_bytes) {
-                byte_presence_kernel<<<296, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
-                                                              engine.flags.as<uint32_t>());
+                byte_presence_kernel<<<2 * device_sms, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
+                                                                         engine.flags.as<uint32_t>());
                 SZB_CUDA(cudaGetLastError());
                 stats.kernel_launches++;
             }
             if (need_queries) {
                 SZB_CUDA(engine.query_flags.reserve(256 * sizeof(uint32_t)));
                 SZB_CUDA(cudaMemsetAsync(engine.query_flags.ptr, 0, 256 * sizeof(uint32_t), stream));
-                byte_presence_kernel<<<296, 512, 0, stream>>>(qs.raw.as<uint8_t>(), qs.total_bytes,
-                                                              engine.query_flags.as<uint32_t>());
+                byte_presence_kernel<<<2 * device_sms, 512, 0, stream>>>(qs.raw.as<uint8_t>(), qs.total_bytes,
+                                                                         engine.query_flags.as<uint32_t>());
                 SZB_CUDA(cudaGetLastError());
                 stats.kernel_launches++;
                 SZB_CUDA(cudaMemcpyAsync(query_present, engine.query_flags.ptr, sizeof(query_present),
@@ -747,116 +812,124 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
         if (engine.utf8)
             for (int b = 128; b < 256; ++b) wide_symbols |= present[b] != 0 || query_present[b] != 0;
     }
+    if (!wide_symbols) return ok();
 
     // 2a. UTF-8 engines: pure-ASCII input is byte-level Levenshtein (as the reference's per-pair ASCII fallback,
     //     serial.hpp:2811-2814); anything else is decoded into UTF-32 symbol streams that replace the byte streams
     //     in everything downstream (lengths, offsets, scheduling), and scored by the symbol-compare recurrences.
-    if (wide_symbols) {
-        auto decode_set = [&](StagedSet &set) -> Failure {
-            uint32_t const count = (uint32_t)set.count;
-            SZB_CUDA(set.rune_counts.reserve((size_t)(count + 1) * sizeof(uint32_t)));
-            SZB_CUDA(set.rune_offsets.reserve((size_t)(count + 1) * sizeof(uint32_t)));
-            int const blocks = (int)((count + 127) / 128);
-            if (count) {
-                utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
-                                                               count, set.rune_counts.as<uint32_t>(), nullptr, nullptr);
-                SZB_CUDA(cudaGetLastError());
-                stats.kernel_launches++;
-            }
-            set.rune_counts_host.resize(count + 1);
-            SZB_CUDA(cudaMemcpyAsync(set.rune_counts_host.data(), set.rune_counts.ptr, (size_t)count * sizeof(uint32_t),
-                                     cudaMemcpyDeviceToHost, stream));
-            SZB_CUDA(cudaStreamSynchronize(stream));
-            stats.d2h_bytes += (size_t)count * sizeof(uint32_t);
-            uint64_t running = 0;
-            set.longest = 0;
-            for (uint32_t i = 0; i < count; ++i) {
-                uint32_t const runes = set.rune_counts_host[i];
-                set.offsets[i] = (uint32_t)running; // from here on, offsets and lengths are in symbols
-                running += runes;
-                set.longest = std::max(set.longest, runes);
-            }
-            set.offsets[count] = (uint32_t)running;
-            SZB_CUDA(cudaMemcpyAsync(set.rune_offsets.ptr, set.offsets.data(), (size_t)(count + 1) * sizeof(uint32_t),
-                                     cudaMemcpyHostToDevice, stream));
-            SZB_CUDA(set.runes.reserve((running + 64) * sizeof(uint32_t)));
-            if (count) {
-                utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
-                                                               count, nullptr, set.rune_offsets.as<uint32_t>(),
-                                                               set.runes.as<uint32_t>());
-                SZB_CUDA(cudaGetLastError());
-                stats.kernel_launches++;
-            }
-            SZB_CUDA(cudaStreamSynchronize(stream)); // `set.offsets` must not change while the copy is in flight
-            return ok();
-        };
-        if (Failure failure = decode_set(qs)) return failure;
+    if (packed) {
+        packed = false;
+        if (Failure failure = upload_raw(qs, stream, stats)) return failure;
         if (!symmetric)
-            if (Failure failure = decode_set(cs)) return failure;
+            if (Failure failure = upload_raw(cs, stream, stats)) return failure;
+    }
+    auto decode_set = [&](StagedSet &set) -> Failure {
+        uint32_t const count = (uint32_t)set.count;
+        SZB_CUDA(set.device_offsets.reserve((size_t)(count + 1) * sizeof(uint32_t)));
+        SZB_CUDA(set.rune_counts.reserve((size_t)(count + 1) * sizeof(uint32_t)));
+        SZB_CUDA(set.rune_offsets.reserve((size_t)(count + 1) * sizeof(uint32_t)));
+        SZB_CUDA(cudaMemcpyAsync(set.device_offsets.ptr, set.offsets.data(), (size_t)(count + 1) * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, stream));
+        stats.h2d_bytes += (size_t)(count + 1) * sizeof(uint32_t);
+        int const blocks = (int)((count + 127) / 128);
+        if (count) {
+            utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
+                                                           count, set.rune_counts.as<uint32_t>(), nullptr, nullptr);
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
+        }
+        set.rune_counts_host.resize(count + 1);
+        SZB_CUDA(cudaMemcpyAsync(set.rune_counts_host.data(), set.rune_counts.ptr, (size_t)count * sizeof(uint32_t),
+                                 cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream)); // also: `set.offsets` is free to change from here on
+        stats.d2h_bytes += (size_t)count * sizeof(uint32_t);
+        uint64_t running = 0;
+        set.longest = 0;
+        for (uint32_t i = 0; i < count; ++i) {
+            uint32_t const runes = set.rune_counts_host[i];
+            set.offsets[i] = (uint32_t)running; // from here on, offsets and lengths are in symbols
+            running += runes;
+            set.longest = std::max(set.longest, runes);
+        }
+        set.offsets[count] = (uint32_t)running;
+        SZB_CUDA(cudaMemcpyAsync(set.rune_offsets.ptr, set.offsets.data(), (size_t)(count + 1) * sizeof(uint32_t),
+                                 cudaMemcpyHostToDevice, stream));
+        SZB_CUDA(set.runes.reserve((running + 64) * sizeof(uint32_t)));
+        if (count) {
+            utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
+                                                           count, nullptr, set.rune_offsets.as<uint32_t>(),
+                                                           set.runes.as<uint32_t>());
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
+        }
+        SZB_CUDA(cudaStreamSynchronize(stream)); // `set.offsets` must not change while the copy is in flight
+        return ok();
+    };
+    if (Failure failure = decode_set(qs)) return failure;
+    if (!symmetric)
+        if (Failure failure = decode_set(cs)) return failure;
 
-        // 2b. At most 256 distinct runes in the whole call? Then rank them into byte ids: the rune problem becomes a
-        //     byte problem over a private alphabet, and every byte-level kernel applies (bit-parallel ones included).
-        SZB_CUDA(engine.rune_table.reserve(kRuneTableSlots * sizeof(uint32_t)));
-        SZB_CUDA(engine.rune_ranks.reserve(kRuneTableSlots * sizeof(uint32_t)));
-        SZB_CUDA(engine.rune_state.reserve(2 * sizeof(uint32_t)));
-        SZB_CUDA(cudaMemsetAsync(engine.rune_table.ptr, 0xFF, kRuneTableSlots * sizeof(uint32_t), stream));
-        SZB_CUDA(cudaMemsetAsync(engine.rune_state.ptr, 0, 2 * sizeof(uint32_t), stream));
-        auto for_each_side = [&](auto &&apply) -> Failure {
-            if (Failure failure = apply(qs)) return failure;
-            if (!symmetric)
-                if (Failure failure = apply(cs)) return failure;
+    // 2b. At most 256 distinct runes in the whole call? Then rank them into byte ids: the rune problem becomes a
+    //     byte problem over a private alphabet, and every byte-level kernel applies (bit-parallel ones included).
+    SZB_CUDA(engine.rune_table.reserve(kRuneTableSlots * sizeof(uint32_t)));
+    SZB_CUDA(engine.rune_ranks.reserve(kRuneTableSlots * sizeof(uint32_t)));
+    SZB_CUDA(engine.rune_state.reserve(2 * sizeof(uint32_t)));
+    SZB_CUDA(cudaMemsetAsync(engine.rune_table.ptr, 0xFF, kRuneTableSlots * sizeof(uint32_t), stream));
+    SZB_CUDA(cudaMemsetAsync(engine.rune_state.ptr, 0, 2 * sizeof(uint32_t), stream));
+    auto for_each_side = [&](auto &&apply) -> Failure {
+        if (Failure failure = apply(qs)) return failure;
+        if (!symmetric)
+            if (Failure failure = apply(cs)) return failure;
+        return ok();
+    };
+    if (Failure failure = for_each_side([&](StagedSet &set) -> Failure {
+            uint64_t const n = set.offsets[set.count];
+            if (!n) return ok();
+            rune_insert_kernel<<<helper_grid(n, 256, device_sms, 8), 256, 0, stream>>>(
+                set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(), engine.rune_state.as<uint32_t>());
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
             return ok();
-        };
-        auto grid_for = [](uint64_t n) { return (int)std::min<uint64_t>((n + 255) / 256, 148 * 8); };
+        }))
+        return failure;
+    rune_rank_kernel<<<1, 1024, 0, stream>>>(engine.rune_table.as<uint32_t>(), engine.rune_ranks.as<uint32_t>(),
+                                             engine.rune_state.as<uint32_t>());
+    SZB_CUDA(cudaGetLastError());
+    stats.kernel_launches++;
+    uint32_t rune_state[2] = {0, 0};
+    SZB_CUDA(cudaMemcpyAsync(rune_state, engine.rune_state.ptr, sizeof(rune_state), cudaMemcpyDeviceToHost, stream));
+    SZB_CUDA(cudaStreamSynchronize(stream));
+    stats.d2h_bytes += sizeof(rune_state);
+    if (rune_state[1] == 0 && rune_state[0] <= 256) {
         if (Failure failure = for_each_side([&](StagedSet &set) -> Failure {
                 uint64_t const n = set.offsets[set.count];
-                if (!n) return ok();
-                rune_insert_kernel<<<grid_for(n), 256, 0, stream>>>(set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(),
-                                                                    engine.rune_state.as<uint32_t>());
-                SZB_CUDA(cudaGetLastError());
-                stats.kernel_launches++;
+                // The id stream overwrites the staged UTF-8 bytes (never longer than them); the symbol offsets (already
+                // in `set.offsets`) become the byte offsets of the byte-level problem.
+                if (n) {
+                    rune_map_kernel<<<helper_grid(n, 256, device_sms, 8), 256, 0, stream>>>(
+                        set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(), engine.rune_ranks.as<uint32_t>(),
+                        set.raw.as<uint8_t>());
+                    SZB_CUDA(cudaGetLastError());
+                    stats.kernel_launches++;
+                }
+                set.total_bytes = n;
+                set.host_view = nullptr;
                 return ok();
             }))
             return failure;
-        rune_rank_kernel<<<1, 1024, 0, stream>>>(engine.rune_table.as<uint32_t>(), engine.rune_ranks.as<uint32_t>(),
-                                                 engine.rune_state.as<uint32_t>());
-        SZB_CUDA(cudaGetLastError());
-        stats.kernel_launches++;
-        uint32_t rune_state[2] = {0, 0};
-        SZB_CUDA(cudaMemcpyAsync(rune_state, engine.rune_state.ptr, sizeof(rune_state), cudaMemcpyDeviceToHost, stream));
-        SZB_CUDA(cudaStreamSynchronize(stream));
-        stats.d2h_bytes += sizeof(rune_state);
-        if (rune_state[1] == 0 && rune_state[0] <= 256) {
-            if (Failure failure = for_each_side([&](StagedSet &set) -> Failure {
-                    uint64_t const n = set.offsets[set.count];
-                    // The id stream overwrites the staged UTF-8 bytes (never longer than them) and the symbol offsets
-                    // become the byte offsets of the byte-level problem.
-                    if (n) {
-                        rune_map_kernel<<<grid_for(n), 256, 0, stream>>>(set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(),
-                                                                         engine.rune_ranks.as<uint32_t>(), set.raw.as<uint8_t>());
-                        SZB_CUDA(cudaGetLastError());
-                        stats.kernel_launches++;
-                    }
-                    SZB_CUDA(cudaMemcpyAsync(set.device_offsets.ptr, set.rune_offsets.ptr, (set.count + 1) * sizeof(uint32_t),
-                                             cudaMemcpyDeviceToDevice, stream));
-                    set.total_bytes = n;
-                    set.host_view = nullptr;
-                    return ok();
-                }))
-                return failure;
-            wide_symbols = false;
-            std::memset(present, 0, sizeof(present));
-            SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
-            SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
-            if (cs.total_bytes) {
-                byte_presence_kernel<<<296, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes, engine.flags.as<uint32_t>());
-                SZB_CUDA(cudaGetLastError());
-                stats.kernel_launches++;
-            }
-            SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
-            SZB_CUDA(cudaStreamSynchronize(stream));
-            stats.d2h_bytes += sizeof(present);
+        wide_symbols = false;
+        std::memset(present, 0, sizeof(present));
+        SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
+        SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
+        if (cs.total_bytes) {
+            byte_presence_kernel<<<2 * device_sms, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
+                                                                     engine.flags.as<uint32_t>());
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
         }
+        SZB_CUDA(cudaMemcpyAsync(present, engine.flags.ptr, sizeof(present), cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream));
+        stats.d2h_bytes += sizeof(present);
     }
     return ok();
 }
@@ -900,15 +973,20 @@ struct Schedule {
     uint64_t cells_total = 0, cells_u16 = 0, cells_myers = 0;
 };
 
+/** Multi-pass slots park one boundary column per query row in per-CTA scratch: a job's block is cut so that its
+ *  scratch stays below this many 32-bit words (16 MB), whatever the row count of the call. */
+constexpr uint64_t kScratchWordsPerJob = 4ull << 20;
+
 /**
  *  @brief Steps 4-6 of a call: order the queries, split the candidates between the bit-parallel tier and the DP tiers,
  *         pair DP candidates into slots, choose shapes, and cut everything into jobs / tasks. Host-only.
+ *  @param n_columns candidates [0, n_columns) take part (all of them, except in a row shard of a symmetric call).
  */
 static Failure build_schedule(Engine const &engine, Model const &model, StagedSet const &qs, StagedSet const &cs,
-                              bool symmetric, bool whole_matrix, size_t row_begin, size_t n_rows,
+                              bool symmetric, bool whole_matrix, size_t row_begin, size_t n_rows, size_t n_columns,
                               uint32_t const (&present)[256], bool wide_symbols, int device_sms, Trace const &trace,
                               Schedule &schedule) {
-    size_t const n_queries = qs.count, n_candidates = cs.count;
+    size_t const n_queries = qs.count, n_candidates = n_columns;
     // 4. Query order: longest first, so that the batches a warp sweeps together have similar lengths and the heavy
     //    jobs start early.
     auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
@@ -948,6 +1026,16 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
         std::sort(keys.begin(), keys.end());
         for (size_t c = 0; c < n_candidates; ++c) by_length[c] = (uint32_t)keys[c];
     }
+    uint64_t query_bytes_in_rows = 0;
+    for (uint32_t q : order) query_bytes_in_rows += query_length(q);
+
+    // A call too small to give every warp of the device a pair of its own is bound by the latency of one sweep, not by
+    // throughput: spread each pair over as many lanes as there are idle ones (more lanes = fewer columns per lane =
+    // a shorter dependent chain per step).
+    uint64_t const device_warps = (uint64_t)device_sms * (kThreads / 32);
+    uint64_t const n_pairs = (uint64_t)n_rows * n_candidates;
+    uint32_t latency_lanes = 1;
+    while (latency_lanes < 32 && n_pairs * latency_lanes * 2 <= device_warps * 32) latency_lanes *= 2;
 
     // 5a. Unit-cost Levenshtein over a compact alphabet: candidates the bit-parallel kernel covers leave the DP tiers.
     std::vector<MyersLaunch> &myers_launches = schedule.myers_launches;
@@ -964,8 +1052,6 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
         for (int b = 0; b < 256; ++b) myers_rows += present[b] != 0;
     }
     if (unit_costs && engine.bit_parallel && !wide_symbols) {
-        uint64_t query_bytes = 0;
-        for (uint32_t q : order) query_bytes += query_length(q);
         std::vector<uint32_t> kept;
         // Shared memory bounds the words per lane: a sixteenth of the SM per warp-private table (sixteen resident
         // warps per CTA), or the whole carve-out for a CTA-shared one.
@@ -978,7 +1064,7 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
             uint32_t const c = by_length[i], length = candidate_length(c);
             // Candidates arrive sorted by length: equal lengths are neighbours, so one remembered answer suffices.
             if (length != remembered_length) {
-                myers_shape_for_length(length, max_words, remembered_words, remembered_lanes);
+                myers_shape_for_length(length, max_words, (int)latency_lanes, remembered_words, remembered_lanes);
                 remembered_length = length;
             }
             int const words = remembered_words, lanes = remembered_lanes;
@@ -996,7 +1082,7 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
                 remembered_launch = &*launch;
             }
             remembered_launch->members.push_back({c, (uint32_t)lanes, rows_needed(c)});
-            cells_myers += (uint64_t)length * query_bytes;
+            cells_myers += (uint64_t)length * query_bytes_in_rows;
         }
         std::reverse(kept.begin(), kept.end()); // back to ascending length for the slot builder
         by_length.swap(kept);
@@ -1005,14 +1091,12 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     // A launch that cannot fill the GPU for ~50 us is folded into the next wider one: padding a few candidates to
     // more words per lane costs less than a dependent launch of its own.
     if (myers_launches.size() > 1) {
-        uint64_t query_bytes = 0;
-        for (uint32_t q : order) query_bytes += query_length(q);
         std::sort(myers_launches.begin(), myers_launches.end(),
                   [](MyersLaunch const &a, MyersLaunch const &b) { return a.words < b.words; });
         for (size_t l = 0; l + 1 < myers_launches.size();) {
             uint64_t cells = 0;
             for (MyersCandidate const &member : myers_launches[l].members)
-                cells += (uint64_t)candidate_length(member.candidate) * query_bytes;
+                cells += (uint64_t)candidate_length(member.candidate) * query_bytes_in_rows;
             if (cells >= 1500000000ull) {
                 ++l;
                 continue;
@@ -1021,7 +1105,7 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
             for (MyersCandidate member : myers_launches[l].members) {
                 uint32_t lanes = 1;
                 while (32u * wider.words * lanes < candidate_length(member.candidate)) lanes *= 2;
-                member.lanes = lanes;
+                member.lanes = std::max(lanes, member.lanes);
                 wider.members.push_back(member);
             }
             myers_launches.erase(myers_launches.begin() + l);
@@ -1044,8 +1128,6 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     host_slots.clear();
     host_slots.reserve(n_dp_candidates);
     uint64_t &cells_total = schedule.cells_total = 0, &cells_u16 = schedule.cells_u16 = 0;
-    uint64_t query_bytes_in_rows = 0;
-    for (uint32_t q : order) query_bytes_in_rows += query_length(q);
     // Register budget (128 per thread) caps the strip width per family: packed affine recurrences keep two strips per
     // lane (36 columns), the 32-bit tier adds the strip's symbols for compare mode (32 linear / 20 affine).
     auto widest_strip = [](int family) {
@@ -1054,7 +1136,7 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
         return family_is_affine(family) ? 36 : 40;
     };
     auto shape_of = [&](int family, uint32_t longest) {
-        Shape shape = shape_for_length(longest);
+        Shape shape = shape_for_length(longest, latency_lanes >= 16 ? 32 : 8);
         int const cap = widest_strip(family);
         if (kStrips[shape.strip_index] > cap) {
             uint32_t const widest = (uint32_t)cap * 32;
@@ -1098,7 +1180,9 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
             if (members.empty()) continue;
             LaunchPlan plan = {family, strip, (uint32_t)host_jobs.size(), 0};
             bool const affine = family_is_affine(family);
-            uint64_t const target_jobs = (uint64_t)device_sms * 8;
+            // The persistent CTAs drain the job list through one counter; the last job of every CTA ends at a different
+            // time, so the tail of a launch idles about half a job per SM: jobs are kept to a few percent of a CTA's share.
+            uint64_t const target_jobs = (uint64_t)device_sms * 24;
             uint64_t const wanted_blocks = (target_jobs + members.size() - 1) / members.size();
             for (uint32_t s : members) {
                 CandSlot const &slot = host_slots[s].slot;
@@ -1110,11 +1194,18 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
                     std::max(rows_needed(slot.c0), slot.c1 != kNoCandidate ? rows_needed(slot.c1) : 0u);
                 uint64_t const rounds_total = (slot_rows + round - 1) / round;
                 uint64_t const blocks = std::max<uint64_t>(1, std::min<uint64_t>(wanted_blocks, rounds_total));
-                uint32_t const block_rows = (uint32_t)((rounds_total + blocks - 1) / blocks) * round;
+                uint32_t block_rows = (uint32_t)((rounds_total + blocks - 1) / blocks) * round;
                 uint32_t const longest = std::max(slot.len0, slot.len1);
+                bool const multi_pass = longest > (uint32_t)shape.coverage();
+                if (multi_pass) {
+                    // Boundary scratch of one job: rows of the block x DP rows of its longest query (x 2 for affine).
+                    uint64_t const per_row = ((uint64_t)longest_query + 1) * (affine ? 2 : 1);
+                    uint64_t const rows_cap = std::max<uint64_t>(round, kScratchWordsPerJob / per_row / round * round);
+                    block_rows = (uint32_t)std::min<uint64_t>(block_rows, rows_cap);
+                }
                 for (uint32_t begin = 0; begin < slot_rows; begin += block_rows) {
                     uint32_t const end = (uint32_t)std::min<uint64_t>(slot_rows, (uint64_t)begin + block_rows);
-                    if (longest > (uint32_t)shape.coverage()) {
+                    if (multi_pass) {
                         uint64_t const rows = (uint64_t)query_length(order[begin]) + 1;
                         uint64_t const words = (uint64_t)(end - begin) * rows * (affine ? 2 : 1);
                         if (words > 0xFFFFFFFFull) return fail(sz_overflow_risk_k, "Boundary scratch too large");
@@ -1131,29 +1222,41 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     return ok();
 }
 
-static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
-                     size_t stride, size_t row_begin, size_t row_end, bool whole_matrix) {
-    Trace const trace;
-    if (scope.kind == Scope::kCpu)
-        return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
-    if (device_sm_code(scope.gpu_device) == 0 && visible_device_count() <= scope.gpu_device)
-        return fail(sz_missing_gpu_k, "No CUDA device is visible");
-    if (device_sm_code(scope.gpu_device) < 100)
-        return fail(sz_missing_gpu_k, "stringzillas_b200 kernels require an sm_100-class (Blackwell) device");
-    if (Failure failure = scope.ensure_stream()) return failure;
-    cudaStream_t const stream = scope.stream;
-    std::lock_guard<std::mutex> engine_lock(engine.mutex);
-    if (Failure failure = ensure_events(engine, scope.gpu_device)) return failure;
+/** Drains the scope's stream and the engine's side streams: after a failure nothing may still be running against
+ *  buffers the next call reuses. */
+static void drain(Engine &engine, cudaStream_t stream) {
+    cudaStreamSynchronize(stream);
+    for (cudaStream_t side : engine.side_streams)
+        if (side) cudaStreamSynchronize(side);
+    cudaGetLastError();
+}
 
+/** Inputs of at most this many bytes (both sides together) that the host can read are class-mapped on the host and
+ *  travel inside the per-call arena: one host-to-device copy, no mapping kernels. */
+constexpr uint64_t kPackedLimit = 256 * 1024;
+/** Pageable result matrices up to this size are fetched through the engine's pinned buffer and scattered by the host. */
+constexpr uint64_t kPinnedDownloadLimit = 8ull << 20;
+
+/**
+ *  @brief Scores query rows [row_begin, row_end) against every candidate and writes `results[q * stride + c]`.
+ *         `candidates.object == nullptr` requests the symmetric self-similarity of the queries: the whole matrix
+ *         (lower triangle scored, upper mirrored) when `whole_matrix`, else — a row shard — the cells
+ *         (query i, candidate j) for i in the range and j < row_end, left for the caller to mirror once every shard is in.
+ */
+static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream, InputView queries_view,
+                               InputView candidates_view, void *results, size_t stride, size_t row_begin, size_t row_end,
+                               bool whole_matrix, size_t base_row) {
+    Trace const trace;
     bool const symmetric = candidates_view.object == nullptr;
     szs_b200_call_stats_t stats = {};
+    int const device_sms = std::max(1, device_facts(scope.gpu_device).sms);
     SZB_CUDA(cudaEventRecord(engine.events[0], stream));
 
-    // 1. Stage both sides.
-    if (Failure failure = stage_set(queries_view, engine.queries, stream, stats)) return failure;
+    // 1. Read both layouts (host work; device-resident offsets are bounced).
+    if (Failure failure = read_layout(queries_view, engine.queries, stream)) return failure;
     StagedSet &caller_queries = engine.queries;
     if (!symmetric)
-        if (Failure failure = stage_set(candidates_view, engine.candidates, stream, stats)) return failure;
+        if (Failure failure = read_layout(candidates_view, engine.candidates, stream)) return failure;
     StagedSet &caller_candidates = symmetric ? engine.queries : engine.candidates;
 
     size_t const caller_rows = caller_queries.count, caller_columns = caller_candidates.count;
@@ -1162,7 +1265,6 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     if (caller_columns && stride < caller_columns)
         return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
     if (row_end == row_begin || caller_columns == 0) {
-        SZB_CUDA(cudaStreamSynchronize(stream));
         engine.stats = stats;
         return ok();
     }
@@ -1170,12 +1272,21 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     if (caller_rows >= 0xFFFFFFF0ull || caller_columns >= 0xFFFFFFF0ull)
         return fail(sz_overflow_risk_k, "Too many strings for one call");
 
+    // Small host-resident inputs never get a copy of their own: the host maps them to classes straight into the arena.
+    bool packed = caller_queries.host_readable && caller_candidates.host_readable &&
+                  caller_queries.total_bytes + (symmetric ? 0 : caller_candidates.total_bytes) <= kPackedLimit;
+    if (!packed) {
+        if (Failure failure = upload_raw(caller_queries, stream, stats)) return failure;
+        if (!symmetric)
+            if (Failure failure = upload_raw(caller_candidates, stream, stats)) return failure;
+    }
     trace.mark("staged");
+
     // 2. Which symbols are we scoring: byte presence for the Levenshtein alphabet, UTF-8 decoding / rune ranking.
     uint32_t present[256] = {0};
     bool wide_symbols = false;
-    if (Failure failure = resolve_symbols(engine, stream, symmetric, caller_queries, caller_candidates, stats, present,
-                                          wide_symbols))
+    if (Failure failure = resolve_symbols(engine, stream, symmetric, packed, device_sms, caller_queries,
+                                          caller_candidates, stats, present, wide_symbols))
         return failure;
     trace.mark("alphabet known");
     Model model;
@@ -1195,48 +1306,13 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     size_t const n_queries = qs.count, n_candidates = cs.count;
     if (swapped) row_begin = 0, row_end = n_queries;
     size_t const n_rows = row_end - row_begin;
+    // A row shard of a symmetric call scores its rows against candidates [0, row_end) only.
+    size_t const n_columns = (symmetric && !whole_matrix) ? row_end : n_candidates;
 
-    SZB_CUDA(engine.scoring.reserve(sizeof(Scoring)));
-    SZB_CUDA(engine.lut.reserve(256));
-    SZB_CUDA(engine.upload_model.reserve(sizeof(Scoring) + 256));
-    std::memcpy(engine.upload_model.ptr, &model.scoring, sizeof(Scoring));
-    std::memcpy((char *)engine.upload_model.ptr + sizeof(Scoring), model.lut, 256);
-    SZB_CUDA(cudaMemcpyAsync(engine.scoring.ptr, engine.upload_model.ptr, sizeof(Scoring), cudaMemcpyHostToDevice,
-                             stream));
-    SZB_CUDA(cudaMemcpyAsync(engine.lut.ptr, (char *)engine.upload_model.ptr + sizeof(Scoring), 256,
-                             cudaMemcpyHostToDevice, stream));
-    stats.h2d_bytes += sizeof(Scoring) + 256;
-
-    // 3. Bytes -> classes (skipped in compare mode, where the kernels read raw bytes).
-    uint8_t const *q_classes = qs.raw.as<uint8_t>(), *c_classes = cs.raw.as<uint8_t>();
-    uint32_t const *q_offsets = qs.device_offsets.as<uint32_t>(), *c_offsets = cs.device_offsets.as<uint32_t>();
-    if (wide_symbols) {
-        q_classes = qs.runes.as<uint8_t>(), c_classes = cs.runes.as<uint8_t>();
-        q_offsets = qs.rune_offsets.as<uint32_t>(), c_offsets = cs.rune_offsets.as<uint32_t>();
-    }
-    if (!model.scoring.compare) {
-        auto map_set = [&](StagedSet &set) -> Failure {
-            if (!set.total_bytes) return ok();
-            uint64_t const vectors = (set.total_bytes + 15) / 16;
-            int const blocks = (int)std::min<uint64_t>((vectors + 255) / 256, 148 * 8);
-            map_classes_kernel<<<blocks, 256, 0, stream>>>(set.raw.as<uint8_t>(), set.classes.as<uint8_t>(),
-                                                           set.total_bytes, engine.lut.as<uint8_t>());
-            SZB_CUDA(cudaGetLastError());
-            stats.kernel_launches++;
-            return ok();
-        };
-        if (Failure failure = map_set(qs)) return failure;
-        if (!symmetric)
-            if (Failure failure = map_set(cs)) return failure;
-        q_classes = qs.classes.as<uint8_t>(), c_classes = cs.classes.as<uint8_t>();
-    }
-
-    trace.mark("classes mapped (async)");
     // 4-6. The schedule: query order, bit-parallel candidates, DP slots and shapes, jobs (pure host work).
-    int const device_sms = std::max(1, device_facts(scope.gpu_device).sms);
     Schedule schedule;
-    if (Failure failure = build_schedule(engine, model, qs, cs, symmetric, whole_matrix, row_begin, n_rows, present,
-                                         wide_symbols, device_sms, trace, schedule))
+    if (Failure failure = build_schedule(engine, model, qs, cs, symmetric, whole_matrix, row_begin, n_rows, n_columns,
+                                         present, wide_symbols, device_sms, trace, schedule))
         return failure;
     std::vector<uint32_t> const &order = schedule.order, &position = schedule.position;
     bool const triangle = schedule.triangle;
@@ -1250,59 +1326,96 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     uint64_t const cells_total = schedule.cells_total, cells_u16 = schedule.cells_u16, cells_myers = schedule.cells_myers;
     auto query_length = [&](uint32_t q) { return qs.offsets[q + 1] - qs.offsets[q]; };
     trace.mark("jobs built");
-    // 7. Upload the work list.
-    std::vector<CandSlot> device_slots(host_slots.size());
-    for (size_t s = 0; s < host_slots.size(); ++s) device_slots[s] = host_slots[s].slot;
-    size_t const order_bytes = order.size() * sizeof(uint32_t), slots_bytes = device_slots.size() * sizeof(CandSlot),
-                 jobs_bytes = host_jobs.size() * sizeof(Job);
-    SZB_CUDA(engine.order.reserve(order_bytes));
-    SZB_CUDA(engine.slots.reserve(slots_bytes));
-    SZB_CUDA(engine.jobs.reserve(jobs_bytes));
-    SZB_CUDA(engine.counters.reserve((plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64));
-    std::vector<MyersCandidate> myers_flat; // the bit-parallel launches' candidate lists, back to back
-    for (MyersLaunch const &launch : myers_launches) myers_flat.insert(myers_flat.end(), launch.members.begin(), launch.members.end());
-    size_t const myers_bytes = myers_flat.size() * sizeof(MyersCandidate), position_bytes = position.size() * sizeof(uint32_t);
-    SZB_CUDA(engine.myers_candidates.reserve(myers_bytes));
-    SZB_CUDA(engine.positions.reserve(position_bytes));
-    SZB_CUDA(engine.upload.reserve(order_bytes + slots_bytes + jobs_bytes + myers_bytes + position_bytes));
-    {
-        // One pinned arena per engine: nothing here needs a host synchronisation (the call's final sync covers it).
-        char *arena = (char *)engine.upload.ptr;
-        size_t cursor = 0;
-        if (myers_bytes) {
-            std::memcpy(arena + cursor, myers_flat.data(), myers_bytes);
-            SZB_CUDA(cudaMemcpyAsync(engine.myers_candidates.ptr, arena + cursor, myers_bytes, cudaMemcpyHostToDevice, stream));
-            cursor += myers_bytes;
-        }
-        if (position_bytes) {
-            std::memcpy(arena + cursor, position.data(), position_bytes);
-            SZB_CUDA(cudaMemcpyAsync(engine.positions.ptr, arena + cursor, position_bytes, cudaMemcpyHostToDevice, stream));
-            cursor += position_bytes;
-        }
-        stats.h2d_bytes += myers_bytes + position_bytes;
-        std::memcpy(arena + cursor, order.data(), order_bytes);
-        SZB_CUDA(cudaMemcpyAsync(engine.order.ptr, arena + cursor, order_bytes, cudaMemcpyHostToDevice, stream));
-        cursor += order_bytes;
-        if (slots_bytes) {
-            std::memcpy(arena + cursor, device_slots.data(), slots_bytes);
-            SZB_CUDA(cudaMemcpyAsync(engine.slots.ptr, arena + cursor, slots_bytes, cudaMemcpyHostToDevice, stream));
-            cursor += slots_bytes;
-            std::memcpy(arena + cursor, host_jobs.data(), jobs_bytes);
-            SZB_CUDA(cudaMemcpyAsync(engine.jobs.ptr, arena + cursor, jobs_bytes, cudaMemcpyHostToDevice, stream));
-        }
-        stats.h2d_bytes += order_bytes + slots_bytes + jobs_bytes;
-    }
-    SZB_CUDA(cudaMemsetAsync(engine.counters.ptr, 0, (plans.size() + myers_launches.size()) * sizeof(uint32_t) + 64, stream));
-    SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
-    if (swapped) {
-        SZB_CUDA(engine.results_home.reserve(n_rows * n_candidates * sizeof(int64_t)));
-    }
-    // Launches overlap on side streams: every plan gets its own per-CTA boundary scratch.
-    if (scratch_words_per_cta)
-        SZB_CUDA(engine.scratch.reserve(scratch_words_per_cta * 4 * (uint64_t)device_sms * plans.size()));
 
+    // 7. The arena: everything the host generated for this call, one host-to-device copy.
+    size_t n_myers = 0;
+    for (MyersLaunch const &launch : myers_launches) n_myers += launch.members.size();
+    size_t const n_counters = plans.size() + myers_launches.size() + 16;
+    bool const map_on_host = packed && !model.scoring.compare;
+    ArenaLayout layout;
+    size_t const at_q_offsets = layout.carve((n_queries + 1) * sizeof(uint32_t));
+    size_t const at_c_offsets = symmetric ? at_q_offsets : layout.carve((n_candidates + 1) * sizeof(uint32_t));
+    size_t const at_scoring = layout.carve(sizeof(Scoring));
+    size_t const at_lut = layout.carve(256);
+    size_t const at_order = layout.carve(order.size() * sizeof(uint32_t));
+    size_t const at_position = layout.carve(position.size() * sizeof(uint32_t));
+    size_t const at_slots = layout.carve(host_slots.size() * sizeof(CandSlot));
+    size_t const at_jobs = layout.carve(host_jobs.size() * sizeof(Job));
+    size_t const at_myers = layout.carve(n_myers * sizeof(MyersCandidate));
+    size_t const at_counters = layout.carve(n_counters * sizeof(uint32_t));
+    size_t const at_q_bytes = packed ? layout.carve(qs.total_bytes + 16) : 0;
+    size_t const at_c_bytes = packed ? (symmetric ? at_q_bytes : layout.carve(cs.total_bytes + 16)) : 0;
+    SZB_CUDA(engine.arena_host.reserve(layout.used));
+    SZB_CUDA(engine.arena_device.reserve(layout.used));
+    char *const host = (char *)engine.arena_host.ptr, *const device = (char *)engine.arena_device.ptr;
+    {
+        std::memcpy(host + at_q_offsets, qs.offsets.data(), (n_queries + 1) * sizeof(uint32_t));
+        if (!symmetric) std::memcpy(host + at_c_offsets, cs.offsets.data(), (n_candidates + 1) * sizeof(uint32_t));
+        std::memcpy(host + at_scoring, &model.scoring, sizeof(Scoring));
+        std::memcpy(host + at_lut, model.lut, 256);
+        std::memcpy(host + at_order, order.data(), order.size() * sizeof(uint32_t));
+        if (!position.empty()) std::memcpy(host + at_position, position.data(), position.size() * sizeof(uint32_t));
+        CandSlot *const slots_out = (CandSlot *)(host + at_slots);
+        for (size_t s = 0; s < host_slots.size(); ++s) slots_out[s] = host_slots[s].slot;
+        if (!host_jobs.empty()) std::memcpy(host + at_jobs, host_jobs.data(), host_jobs.size() * sizeof(Job));
+        MyersCandidate *myers_out = (MyersCandidate *)(host + at_myers);
+        for (MyersLaunch const &launch : myers_launches) {
+            std::memcpy(myers_out, launch.members.data(), launch.members.size() * sizeof(MyersCandidate));
+            myers_out += launch.members.size();
+        }
+        std::memset(host + at_counters, 0, n_counters * sizeof(uint32_t));
+        if (packed) {
+            auto pack = [&](StagedSet const &set, size_t at) {
+                uint8_t *const out = (uint8_t *)(host + at);
+                set.for_each_host_string([&](uint8_t const *start, size_t length, size_t i) {
+                    uint8_t *const to = out + set.offsets[i];
+                    if (map_on_host)
+                        for (size_t k = 0; k < length; ++k) to[k] = model.lut[start[k]];
+                    else if (length) std::memcpy(to, start, length);
+                });
+            };
+            pack(qs, at_q_bytes);
+            if (!symmetric) pack(cs, at_c_bytes);
+        }
+    }
+    SZB_CUDA(cudaMemcpyAsync(device, host, layout.used, cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += layout.used;
+    uint32_t const *q_offsets = (uint32_t const *)(device + at_q_offsets), *c_offsets = (uint32_t const *)(device + at_c_offsets);
+    Scoring const *const device_scoring = (Scoring const *)(device + at_scoring);
+    uint32_t const *const device_order = (uint32_t const *)(device + at_order);
+    uint32_t *const device_counters = (uint32_t *)(device + at_counters);
+
+    // 3. Bytes -> classes (skipped in compare mode, where the kernels read raw bytes or symbols).
+    uint8_t const *q_classes, *c_classes;
+    if (packed) q_classes = (uint8_t const *)(device + at_q_bytes), c_classes = (uint8_t const *)(device + at_c_bytes);
+    else if (wide_symbols) q_classes = qs.runes.as<uint8_t>(), c_classes = cs.runes.as<uint8_t>();
+    else if (model.scoring.compare) q_classes = qs.raw.as<uint8_t>(), c_classes = cs.raw.as<uint8_t>();
+    else {
+        auto map_set = [&](StagedSet &set) -> Failure {
+            if (!set.total_bytes) return ok();
+            uint64_t const vectors = (set.total_bytes + 15) / 16;
+            map_classes_kernel<<<helper_grid(vectors, 256, device_sms, 8), 256, 0, stream>>>(
+                set.raw.as<uint8_t>(), set.classes.as<uint8_t>(), set.total_bytes, (uint8_t const *)(device + at_lut));
+            SZB_CUDA(cudaGetLastError());
+            stats.kernel_launches++;
+            return ok();
+        };
+        if (Failure failure = map_set(qs)) return failure;
+        if (!symmetric)
+            if (Failure failure = map_set(cs)) return failure;
+        q_classes = qs.classes.as<uint8_t>(), c_classes = cs.classes.as<uint8_t>();
+    }
     trace.mark("work list uploaded");
-    // 8. Launch: one persistent grid per (family, strip width), all on the scope's stream.
+
+    SZB_CUDA(engine.results.reserve(n_rows * n_candidates * sizeof(int64_t)));
+    if (swapped) SZB_CUDA(engine.results_home.reserve(n_rows * n_candidates * sizeof(int64_t)));
+    // Launches overlap on side streams: every plan gets its own per-CTA boundary scratch, one slab per resident CTA.
+    std::vector<uint64_t> scratch_base(plans.size() + 1, 0);
+    for (size_t p = 0; p < plans.size(); ++p)
+        scratch_base[p + 1] = scratch_base[p] + scratch_words_per_cta * std::min<uint64_t>(plans[p].n_jobs, (uint64_t)device_sms);
+    if (scratch_words_per_cta) SZB_CUDA(engine.scratch.reserve(scratch_base.back() * 4));
+
+    // 8. Launch: one persistent grid per (family, strip width) and per bit-parallel word count.
     SZB_CUDA(cudaEventRecord(engine.events[1], stream));
     size_t const n_launches = myers_launches.size() + plans.size();
     bool const fan_out = n_launches > 1;
@@ -1338,13 +1451,13 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
             MyersArgs args;
             args.q_cls = q_classes, args.q_off = q_offsets;
             args.c_cls = c_classes, args.c_off = c_offsets;
-            args.q_order = engine.order.as<uint32_t>();
-            args.candidates = engine.myers_candidates.as<MyersCandidate>() + first;
+            args.q_order = device_order;
+            args.candidates = (MyersCandidate const *)(device + at_myers) + first;
             args.n_candidates = (uint32_t)launch.members.size();
             args.n_rows = (uint32_t)n_rows;
             args.blocks_per_candidate = (uint32_t)blocks;
             args.batches_per_block = (uint32_t)batches_per_block;
-            args.task_counter = engine.counters.as<uint32_t>() + plans.size() + l;
+            args.task_counter = device_counters + plans.size() + l;
             args.n_classes = model.scoring.n_classes;
             args.results = engine.results.as<int64_t>();
             args.stride = n_candidates;
@@ -1364,16 +1477,16 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         args.q_cls = q_classes, args.q_off = q_offsets;
         args.c_cls = c_classes, args.c_off = c_offsets;
         args.wide_symbols = wide_symbols ? 1u : 0u;
-        args.q_order = engine.order.as<uint32_t>();
-        args.slots = engine.slots.as<CandSlot>();
-        args.jobs = engine.jobs.as<Job>() + plan.first_job;
+        args.q_order = device_order;
+        args.slots = (CandSlot const *)(device + at_slots);
+        args.jobs = (Job const *)(device + at_jobs) + plan.first_job;
         args.n_jobs = plan.n_jobs;
-        args.job_counter = engine.counters.as<uint32_t>() + p;
-        args.scoring = engine.scoring.as<Scoring>();
+        args.job_counter = device_counters + p;
+        args.scoring = device_scoring;
         args.results = engine.results.as<int64_t>();
         args.stride = n_candidates;
         args.row_base = (uint32_t)row_begin;
-        args.scratch = engine.scratch.as<uint32_t>() + p * scratch_words_per_cta * (uint64_t)device_sms;
+        args.scratch = engine.scratch.as<uint32_t>() + scratch_base[p];
         args.scratch_words_per_cta = scratch_words_per_cta;
         int const grid = (int)std::min<uint32_t>(plan.n_jobs, (uint32_t)device_sms);
         size_t const smem = shared_bytes(plan.strip_index, model.scoring.n_classes, model.scoring.compare != 0);
@@ -1387,38 +1500,51 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
         }
     if (symmetric && whole_matrix && n_queries > 1) {
         uint64_t const total = (uint64_t)n_queries * n_queries;
-        int const blocks = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);
+        int const blocks = helper_grid(total, 256, device_sms, 16);
         if (triangle)
             mirror_ranked_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates,
-                                                             engine.positions.as<uint32_t>());
+                                                             (uint32_t const *)(device + at_position));
         else
             mirror_lower_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates);
         SZB_CUDA(cudaGetLastError());
         stats.kernel_launches++;
     }
-    SZB_CUDA(cudaEventRecord(engine.events[2], stream));
-
-    trace.mark("kernels launched");
-    // 9. Results home: a strided 2-D copy into the caller's matrix (host, pinned, managed or device memory).
+    int64_t const *home = engine.results.as<int64_t>();
     if (swapped) {
         uint64_t const total = (uint64_t)caller_rows * caller_columns;
-        int const blocks = (int)std::min<uint64_t>((total + 255) / 256, 148 * 16);
-        transpose_results_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(),
-                                                             engine.results_home.as<int64_t>(), caller_rows, caller_columns);
+        transpose_results_kernel<<<helper_grid(total, 256, device_sms, 16), 256, 0, stream>>>(
+            engine.results.as<int64_t>(), engine.results_home.as<int64_t>(), caller_rows, caller_columns);
         SZB_CUDA(cudaGetLastError());
         stats.kernel_launches++;
-        SZB_CUDA(cudaMemcpy2DAsync(results, stride * sizeof(int64_t), engine.results_home.ptr,
-                                   caller_columns * sizeof(int64_t), caller_columns * sizeof(int64_t), caller_rows,
-                                   cudaMemcpyDefault, stream));
+        home = engine.results_home.as<int64_t>();
+    }
+    SZB_CUDA(cudaEventRecord(engine.events[2], stream));
+    trace.mark("kernels launched");
+
+    // 9. Results home: a strided 2-D copy into the caller's matrix (host, pinned, managed or device memory). Small
+    //    pageable destinations are served through the engine's pinned buffer: one true DMA, then a host scatter.
+    size_t const home_rows = swapped ? caller_rows : n_rows, home_columns = swapped ? caller_columns : n_columns;
+    size_t const home_pitch = (swapped ? caller_columns : n_candidates) * sizeof(int64_t);
+    int64_t *const destination = (int64_t *)results + (swapped ? 0 : row_begin - base_row) * stride;
+    MemoryKind const results_kind = memory_kind(results);
+    uint64_t const home_bytes = (uint64_t)home_rows * home_columns * sizeof(int64_t);
+    bool const through_pinned = results_kind == MemoryKind::kPageable && home_bytes <= kPinnedDownloadLimit;
+    if (through_pinned) {
+        SZB_CUDA(engine.download.reserve(home_bytes));
+        SZB_CUDA(cudaMemcpy2DAsync(engine.download.ptr, home_columns * sizeof(int64_t), home, home_pitch,
+                                   home_columns * sizeof(int64_t), home_rows, cudaMemcpyDeviceToHost, stream));
     }
     else {
-        SZB_CUDA(cudaMemcpy2DAsync((int64_t *)results + row_begin * stride, stride * sizeof(int64_t), engine.results.ptr,
-                                   n_candidates * sizeof(int64_t), n_candidates * sizeof(int64_t), n_rows,
-                                   cudaMemcpyDefault, stream));
+        SZB_CUDA(cudaMemcpy2DAsync(destination, stride * sizeof(int64_t), home, home_pitch,
+                                   home_columns * sizeof(int64_t), home_rows, cudaMemcpyDefault, stream));
     }
-    if (pointer_is_host_readable(results)) stats.d2h_bytes += n_rows * n_candidates * sizeof(int64_t);
+    if (results_kind != MemoryKind::kDevice) stats.d2h_bytes += home_bytes;
     SZB_CUDA(cudaEventRecord(engine.events[3], stream));
     SZB_CUDA(cudaStreamSynchronize(stream));
+    if (through_pinned)
+        for (size_t r = 0; r < home_rows; ++r)
+            std::memcpy(destination + r * stride, (int64_t const *)engine.download.ptr + r * home_columns,
+                        home_columns * sizeof(int64_t));
 
     trace.mark("stream drained");
     float kernel_ms = 0, total_ms = 0;
@@ -1435,6 +1561,28 @@ static Failure cross(Engine &engine, Scope &scope, InputView queries_view, Input
     stats.pairs_u16 = cells_u16, stats.pairs_s32 = cells_total - cells_u16 - cells_myers, stats.pairs_bit_parallel = cells_myers;
     engine.stats = stats;
     return ok();
+}
+
+/** @param base_row the matrix row `results` points at: 0 for a full-shape matrix, `row_begin` for a compact slab. */
+static Failure cross(Engine &engine, Scope &scope, InputView queries_view, InputView candidates_view, void *results,
+                     size_t stride, size_t row_begin, size_t row_end, bool whole_matrix, size_t base_row = 0) {
+    if (scope.kind == Scope::kCpu)
+        return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
+    if (device_sm_code(scope.gpu_device) == 0 && visible_device_count() <= scope.gpu_device)
+        return fail(sz_missing_gpu_k, "No CUDA device is visible");
+    if (device_sm_code(scope.gpu_device) < 100)
+        return fail(sz_missing_gpu_k, "stringzillas_b200 kernels require an sm_100-class (Blackwell) device");
+    if (Failure failure = scope.ensure_stream()) return failure;
+    std::lock_guard<std::mutex> engine_lock(engine.mutex);
+    if (Failure failure = ensure_events(engine, scope.gpu_device)) return failure;
+    Failure failure = cross_unguarded(engine, scope, scope.stream, queries_view, candidates_view, results, stride,
+                                      row_begin, row_end, whole_matrix, whole_matrix ? 0 : base_row);
+    if (failure) {
+        // Launches of this call may still be in flight on the scope's stream or the side streams.
+        drain(engine, scope.stream);
+        engine.stats = {};
+    }
+    return failure;
 }
 
 #pragma endregion
@@ -1460,6 +1608,420 @@ cudaError_t launch_wavefront(int family, int shape, int grid, size_t smem, cudaS
 
 } // namespace szb
 
+#pragma region Multi-GPU
+
+namespace szb {
+
+/**
+ *  Contiguous blocks of query rows of near-equal cost: a row costs `len(q) * sum(len(c))`, so blocks
+ *  balance the total query length; for a symmetric call only the cells left of the diagonal are scored, so row i weighs
+ *  `len(i) * sum(len(j), j <= i)`. Every row weighs at least 1 so that empty strings still spread over the parts.
+ *  Writes `parts + 1` bounds; deterministic, so every rank of a communicator computes the same partition.
+ */
+static void partition_rows(uint64_t const *lengths, size_t count, size_t parts, bool symmetric, uint64_t *bounds) {
+    std::vector<long double> cumulative(count + 1, 0);
+    long double prefix = 0;
+    for (size_t i = 0; i < count; ++i) {
+        long double const length = (long double)std::max<uint64_t>(lengths[i], 1);
+        prefix += length;
+        cumulative[i + 1] = cumulative[i] + (symmetric ? length * prefix : length);
+    }
+    bounds[0] = 0;
+    for (size_t part = 1; part < parts; ++part) {
+        long double const target = cumulative[count] * (long double)part / (long double)parts;
+        size_t const cut = (size_t)(std::lower_bound(cumulative.begin(), cumulative.end(), target) - cumulative.begin());
+        bounds[part] = std::min<uint64_t>(std::max<uint64_t>(cut, bounds[part - 1]), count);
+    }
+    bounds[parts] = count;
+}
+
+/** Host-readable copy of a u64 tape's string lengths (device-resident offsets are fetched once). */
+static Failure tape_lengths(sz_sequence_u64tape_t const *tape, std::vector<uint64_t> &lengths) {
+    size_t const count = (size_t)tape->count;
+    lengths.assign(count, 0);
+    if (!count) return ok();
+    if (!tape->offsets) return fail(sz_unexpected_dimensions_k, "Tape offsets are null");
+    std::vector<uint64_t> bounce;
+    uint64_t const *offsets = (uint64_t const *)tape->offsets;
+    if (!pointer_is_host_readable(offsets)) {
+        bounce.resize(count + 1);
+        SZB_CUDA(cudaMemcpy(bounce.data(), offsets, (count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        offsets = bounce.data();
+    }
+    for (size_t i = 0; i < count; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail(sz_unexpected_dimensions_k, "Tape offsets decrease");
+        lengths[i] = offsets[i + 1] - offsets[i];
+    }
+    return ok();
+}
+
+/** Mirrors the lower triangle of a host-resident square matrix into the upper one, rows [begin, end), tile by tile. */
+static void mirror_lower_on_host(int64_t *matrix, size_t n, size_t stride, size_t begin, size_t end) {
+    constexpr size_t tile = 32;
+    for (size_t i0 = begin; i0 < end; i0 += tile)
+        for (size_t j0 = i0; j0 < n; j0 += tile)
+            for (size_t i = i0; i < std::min(i0 + tile, end); ++i)
+                for (size_t j = std::max(j0, i + 1); j < std::min(j0 + tile, n); ++j) matrix[i * stride + j] = matrix[j * stride + i];
+}
+
+/**
+ *  The GPUs of one box driven together from ONE process: a scope (device + stream) and a parked host thread per GPU.
+ *  The reference's scope constructor takes a single device id (stringzillas.h:137-138) and allows different scopes to
+ *  be used from different host threads (types.cuh:433-444); this is the orchestrator SURVEY.md §8e asks for on top.
+ */
+struct DeviceGroup {
+    std::vector<std::unique_ptr<Scope>> scopes;
+    std::vector<std::thread> workers;
+    std::mutex mutex;
+    std::condition_variable wake, finished;
+    uint64_t generation = 0;
+    size_t pending = 0;
+    bool stopping = false;
+    void (*task)(void *, size_t) = nullptr;
+    void *task_context = nullptr;
+    std::mutex call_mutex; // one sharded call at a time per group
+
+    ~DeviceGroup() {
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            stopping = true;
+        }
+        wake.notify_all();
+        for (std::thread &worker : workers) worker.join();
+    }
+    void start() {
+        for (size_t index = 1; index < scopes.size(); ++index)
+            workers.emplace_back([this, index] {
+                uint64_t seen = 0;
+                for (;;) {
+                    void (*run)(void *, size_t);
+                    void *context;
+                    {
+                        std::unique_lock<std::mutex> lock(mutex);
+                        wake.wait(lock, [&] { return stopping || generation != seen; });
+                        if (stopping) return;
+                        seen = generation, run = task, context = task_context;
+                    }
+                    run(context, index);
+                    {
+                        std::lock_guard<std::mutex> lock(mutex);
+                        --pending;
+                    }
+                    finished.notify_one();
+                }
+            });
+    }
+    /** Runs `run(context, i)` for every member: member 0 on the calling thread, the others on their parked threads. */
+    void run_on_all(void (*run)(void *, size_t), void *context) {
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            task = run, task_context = context, pending = workers.size(), ++generation;
+        }
+        wake.notify_all();
+        run(context, 0);
+        std::unique_lock<std::mutex> lock(mutex);
+        finished.wait(lock, [&] { return pending == 0; });
+    }
+};
+
+struct ShardedCall {
+    Engine *engine;
+    DeviceGroup *group;
+    sz_sequence_u64tape_t const *queries, *candidates;
+    void *results;
+    size_t stride;
+    std::vector<uint64_t> bounds;
+    std::vector<Failure> failures;
+    bool mirror_on_host = false;
+    size_t n = 0;
+};
+
+static void run_shard(void *context, size_t index) {
+    ShardedCall &call = *static_cast<ShardedCall *>(context);
+    Engine &engine = index == 0 ? *call.engine : *call.engine->shards[index - 1];
+    InputView q {InputView::kTape64, call.queries}, c {InputView::kTape64, call.candidates};
+    size_t const begin = (size_t)call.bounds[index], end = (size_t)call.bounds[index + 1];
+    bool const whole = call.group->scopes.size() == 1;
+    call.failures[index] = cross(engine, *call.group->scopes[index], q, c, call.results, call.stride, begin, end, whole);
+}
+
+static void mirror_shard(void *context, size_t index) {
+    ShardedCall &call = *static_cast<ShardedCall *>(context);
+    mirror_lower_on_host((int64_t *)call.results, call.n, call.stride, (size_t)call.bounds[index], (size_t)call.bounds[index + 1]);
+}
+
+/**
+ *  One cross product over all the GPUs of a group: rows are partitioned by cost, every shard copies the inputs it needs
+ *  straight from the caller's memory and writes its rows straight into the caller's matrix. No collective is involved:
+ *  host-originated data reaches each GPU over its own PCIe link.
+ */
+static Failure sharded_cross(Engine &engine, DeviceGroup &group, sz_sequence_u64tape_t const *queries,
+                             sz_sequence_u64tape_t const *candidates, void *results, size_t stride) {
+    std::lock_guard<std::mutex> call_lock(group.call_mutex);
+    size_t const parts = group.scopes.size();
+    while (engine.shards.size() + 1 < parts) {
+        std::unique_ptr<Engine> shard = engine.clone();
+        if (!shard) return fail(sz_bad_alloc_k, "Failed to allocate an engine shard");
+        engine.shards.push_back(std::move(shard));
+    }
+    for (size_t i = 0; i + 1 < parts; ++i) engine.shards[i]->bit_parallel = engine.bit_parallel;
+    ShardedCall call;
+    call.engine = &engine, call.group = &group, call.queries = queries, call.candidates = candidates;
+    call.results = results, call.stride = stride, call.n = (size_t)queries->count;
+    std::vector<uint64_t> lengths;
+    if (Failure failure = tape_lengths(queries, lengths)) return failure;
+    bool const symmetric = candidates == nullptr;
+    call.bounds.resize(parts + 1);
+    partition_rows(lengths.data(), lengths.size(), parts, symmetric, call.bounds.data());
+    call.failures.assign(parts, Failure {});
+    auto const start = std::chrono::steady_clock::now();
+    group.run_on_all(&run_shard, &call);
+    for (Failure const &failure : call.failures)
+        if (failure) return failure;
+    // Row shards of a symmetric call leave the cells right of the diagonal to this mirror (serial.hpp:3183-3184).
+    if (symmetric && parts > 1 && call.n > 1) {
+        if (pointer_is_host_readable(results)) group.run_on_all(&mirror_shard, &call);
+        else {
+            Scope &scope = *group.scopes[0];
+            SZB_CUDA(cudaSetDevice(scope.gpu_device));
+            int const sms = std::max(1, device_facts(scope.gpu_device).sms);
+            mirror_lower_kernel<<<helper_grid((uint64_t)call.n * call.n, 256, sms, 16), 256, 0, scope.stream>>>(
+                (int64_t *)results, call.n, stride);
+            SZB_CUDA(cudaGetLastError());
+            SZB_CUDA(cudaStreamSynchronize(scope.stream));
+        }
+    }
+    double const wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - start).count();
+    // Telemetry of the whole call: the slowest shard's kernels, everything summed.
+    szs_b200_call_stats_t total = engine.stats;
+    for (size_t i = 0; i + 1 < parts; ++i) {
+        szs_b200_call_stats_t const &shard = engine.shards[i]->stats;
+        total.kernel_milliseconds = std::max(total.kernel_milliseconds, shard.kernel_milliseconds);
+        total.cells += shard.cells, total.kernel_launches += shard.kernel_launches;
+        total.h2d_bytes += shard.h2d_bytes, total.d2h_bytes += shard.d2h_bytes;
+        total.pairs_u16 += shard.pairs_u16, total.pairs_s32 += shard.pairs_s32, total.pairs_bit_parallel += shard.pairs_bit_parallel;
+    }
+    if (parts > 1) total.total_milliseconds = wall_ms;
+    engine.stats = total;
+    return ok();
+}
+
+/* ---- One process per GPU: the exchange step over NCCL, issued from C ------------------------------------------- */
+
+/** The handful of NCCL entry points the exchange needs, resolved at run time from the NCCL already in the process
+ *  (torch's, under torch.distributed.run) or from `SZS_B200_NCCL_LIBRARY` / the system's libnccl.so.2. The library
+ *  must load and score on one GPU without NCCL installed, so nothing here is a link-time dependency. */
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(void const *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(void const *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    char const *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ready() const { return GroupEnd != nullptr; }
+};
+
+static NcclApi const &nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        char const *override_path = std::getenv("SZS_B200_NCCL_LIBRARY");
+        void *handle = override_path ? dlopen(override_path, RTLD_NOW | RTLD_GLOBAL) : nullptr;
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD); // the copy torch brought along
+        if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) return;
+        NcclApi loaded;
+        loaded.handle = handle;
+        loaded.GetUniqueId = (decltype(loaded.GetUniqueId))dlsym(handle, "ncclGetUniqueId");
+        loaded.CommInitRank = (decltype(loaded.CommInitRank))dlsym(handle, "ncclCommInitRank");
+        loaded.CommDestroy = (decltype(loaded.CommDestroy))dlsym(handle, "ncclCommDestroy");
+        loaded.Broadcast = (decltype(loaded.Broadcast))dlsym(handle, "ncclBroadcast");
+        loaded.Send = (decltype(loaded.Send))dlsym(handle, "ncclSend");
+        loaded.Recv = (decltype(loaded.Recv))dlsym(handle, "ncclRecv");
+        loaded.GroupStart = (decltype(loaded.GroupStart))dlsym(handle, "ncclGroupStart");
+        loaded.GetErrorString = (decltype(loaded.GetErrorString))dlsym(handle, "ncclGetErrorString");
+        loaded.GroupEnd = (decltype(loaded.GroupEnd))dlsym(handle, "ncclGroupEnd");
+        if (loaded.GetUniqueId && loaded.CommInitRank && loaded.CommDestroy && loaded.Broadcast && loaded.Send &&
+            loaded.Recv && loaded.GroupStart && loaded.GroupEnd && loaded.GetErrorString)
+            api = loaded;
+    });
+    return api;
+}
+
+#define SZB_NCCL(call)                                                       \
+    do {                                                                     \
+        ncclResult_t result_ = (call);                                       \
+        if (result_ != ncclSuccess) return fail(sz_status_unknown_k, nccl_api().GetErrorString(result_)); \
+    } while (0)
+
+/** One rank of a row-sharded job: an NCCL communicator over the ranks' GPUs plus the exchange buffers. */
+struct Communicator {
+    ncclComm_t comm = nullptr;
+    int world = 1, rank = 0, device = 0;
+    DeviceBuffer header, payload, gathered;
+    PinnedBuffer header_host, payload_host;
+    std::vector<uint64_t> q_offsets, c_offsets, bounds;
+    ~Communicator() {
+        if (comm && nccl_api().ready()) nccl_api().CommDestroy(comm);
+    }
+};
+
+constexpr size_t kHeaderWords = 8;
+constexpr uint64_t kHeaderMagic = 0x30303242535A53ull; // "SZSB200"
+
+/**
+ *  @brief One cross product over the ranks of a communicator. Rank 0 owns the inputs (host or device memory) and
+ *         receives the whole score matrix; the other ranks pass null tapes and results.
+ *
+ *  The only collectives are ONE broadcast of the packed inputs (a 64-byte header first, so that the other ranks can
+ *  size the payload) and ONE gather of the score slabs (grouped send/recv, no padding), both on the scope's stream;
+ *  every pair is independent, so nothing crosses GPUs during the DP itself.
+ */
+static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &communicator,
+                                  sz_sequence_u64tape_t const *queries, sz_sequence_u64tape_t const *candidates,
+                                  void *results, size_t stride) {
+    NcclApi const &nccl = nccl_api();
+    if (!nccl.ready() || !communicator.comm) return fail(sz_status_unknown_k, "NCCL communicator is not initialised");
+    if (scope.kind == Scope::kCpu) return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
+    if (Failure failure = scope.ensure_stream()) return failure;
+    cudaStream_t const stream = scope.stream;
+    bool const root = communicator.rank == 0;
+    int const world = communicator.world;
+    SZB_CUDA(communicator.header.reserve(kHeaderWords * sizeof(uint64_t)));
+    SZB_CUDA(communicator.header_host.reserve(kHeaderWords * sizeof(uint64_t)));
+    uint64_t *const header = (uint64_t *)communicator.header_host.ptr;
+
+    // 1. Rank 0 packs both tapes into one message: offsets (relative, 64-bit) first, then the bytes.
+    uint64_t n_q = 0, n_c = 0, bytes_q = 0, bytes_c = 0, symmetric = 0, q_first = 0, c_first = 0;
+    if (root) {
+        if (!queries) return fail(sz_status_unknown_k, "Rank 0 must pass the queries");
+        symmetric = candidates == nullptr;
+        auto measure = [](sz_sequence_u64tape_t const *tape, std::vector<uint64_t> &relative, uint64_t &bytes,
+                          uint64_t &first) -> Failure {
+            size_t const count = (size_t)tape->count;
+            relative.assign(count + 1, 0);
+            bytes = 0, first = 0;
+            if (!count) return ok();
+            if (!tape->offsets) return fail(sz_unexpected_dimensions_k, "Tape offsets are null");
+            std::vector<uint64_t> bounce;
+            uint64_t const *offsets = (uint64_t const *)tape->offsets;
+            if (!pointer_is_host_readable(offsets)) {
+                bounce.resize(count + 1);
+                SZB_CUDA(cudaMemcpy(bounce.data(), offsets, (count + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+                offsets = bounce.data();
+            }
+            for (size_t i = 0; i <= count; ++i) {
+                if (i && offsets[i] < offsets[i - 1]) return fail(sz_unexpected_dimensions_k, "Tape offsets decrease");
+                relative[i] = offsets[i] - offsets[0];
+            }
+            bytes = relative[count], first = offsets[0];
+            return ok();
+        };
+        n_q = queries->count;
+        if (Failure failure = measure(queries, communicator.q_offsets, bytes_q, q_first)) return failure;
+        if (!symmetric) {
+            n_c = candidates->count;
+            if (Failure failure = measure(candidates, communicator.c_offsets, bytes_c, c_first)) return failure;
+        }
+        header[0] = kHeaderMagic, header[1] = n_q, header[2] = n_c, header[3] = bytes_q, header[4] = bytes_c;
+        header[5] = symmetric, header[6] = header[7] = 0;
+        SZB_CUDA(cudaMemcpyAsync(communicator.header.ptr, header, kHeaderWords * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+    }
+    SZB_NCCL(nccl.Broadcast(communicator.header.ptr, communicator.header.ptr, kHeaderWords * sizeof(uint64_t), ncclUint8, 0,
+                            communicator.comm, stream));
+    if (!root) {
+        SZB_CUDA(cudaMemcpyAsync(header, communicator.header.ptr, kHeaderWords * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA(cudaStreamSynchronize(stream));
+        if (header[0] != kHeaderMagic) return fail(sz_status_unknown_k, "Malformed exchange header");
+        n_q = header[1], n_c = header[2], bytes_q = header[3], bytes_c = header[4], symmetric = header[5];
+    }
+    size_t const offsets_bytes = (size_t)((n_q + 1) + (symmetric ? 0 : n_c + 1)) * sizeof(uint64_t);
+    size_t const at_q_bytes = (offsets_bytes + 15) & ~(size_t)15;
+    size_t const at_c_bytes = (at_q_bytes + bytes_q + 15) & ~(size_t)15;
+    size_t const payload_bytes = ((at_c_bytes + bytes_c + 15) & ~(size_t)15) + 16;
+    SZB_CUDA(communicator.payload.reserve(payload_bytes));
+    char *const payload = (char *)communicator.payload.ptr;
+    if (root) {
+        // Offsets go through a pinned buffer; the bytes are copied from wherever the caller keeps them.
+        SZB_CUDA(communicator.payload_host.reserve(offsets_bytes));
+        uint64_t *const packed = (uint64_t *)communicator.payload_host.ptr;
+        std::memcpy(packed, communicator.q_offsets.data(), (n_q + 1) * sizeof(uint64_t));
+        if (!symmetric) std::memcpy(packed + n_q + 1, communicator.c_offsets.data(), (n_c + 1) * sizeof(uint64_t));
+        SZB_CUDA(cudaMemcpyAsync(payload, packed, offsets_bytes, cudaMemcpyHostToDevice, stream));
+        if (bytes_q)
+            SZB_CUDA(cudaMemcpyAsync(payload + at_q_bytes, (char const *)queries->data + q_first, bytes_q, cudaMemcpyDefault, stream));
+        if (!symmetric && bytes_c) {
+            SZB_CUDA(cudaMemcpyAsync(payload + at_c_bytes, (char const *)candidates->data + c_first, bytes_c, cudaMemcpyDefault, stream));
+        }
+    }
+    SZB_NCCL(nccl.Broadcast(payload, payload, payload_bytes, ncclUint8, 0, communicator.comm, stream));
+    if (!root) {
+        communicator.q_offsets.resize(n_q + 1);
+        SZB_CUDA(cudaMemcpyAsync(communicator.q_offsets.data(), payload, (n_q + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        if (!symmetric) {
+            communicator.c_offsets.resize(n_c + 1);
+            SZB_CUDA(cudaMemcpyAsync(communicator.c_offsets.data(), payload + (n_q + 1) * sizeof(uint64_t),
+                                     (n_c + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        }
+        SZB_CUDA(cudaStreamSynchronize(stream));
+    }
+
+    // 2. Every rank scores its block of rows against the device-resident copy.
+    size_t const columns = symmetric ? (size_t)n_q : (size_t)n_c;
+    std::vector<uint64_t> lengths(n_q);
+    for (size_t i = 0; i < n_q; ++i) lengths[i] = communicator.q_offsets[i + 1] - communicator.q_offsets[i];
+    communicator.bounds.resize(world + 1);
+    partition_rows(lengths.data(), (size_t)n_q, (size_t)world, symmetric != 0, communicator.bounds.data());
+    size_t const begin = (size_t)communicator.bounds[communicator.rank], end = (size_t)communicator.bounds[communicator.rank + 1];
+    sz_sequence_u64tape_t local_q {payload + at_q_bytes, communicator.q_offsets.data(), (sz_size_t)n_q};
+    sz_sequence_u64tape_t local_c {payload + at_c_bytes, communicator.c_offsets.data(), (sz_size_t)n_c};
+    InputView q {InputView::kTape64, &local_q}, c {InputView::kTape64, symmetric ? nullptr : &local_c};
+    // Rank 0 assembles the whole matrix on its device; the others keep only their slab.
+    size_t const slab_rows = root ? (size_t)n_q : end - begin;
+    SZB_CUDA(communicator.gathered.reserve(std::max<size_t>(slab_rows * columns, 1) * sizeof(int64_t)));
+    int64_t *const slab = communicator.gathered.as<int64_t>();
+    bool const whole = world == 1;
+    if (n_q && columns)
+        if (Failure failure = cross(engine, scope, q, c, slab, columns, begin, end, whole, root ? 0 : begin)) return failure;
+
+    // 3. One gather of the slabs (rows x columns of int64, contiguous on both ends).
+    if (world > 1 && columns) {
+        SZB_NCCL(nccl.GroupStart());
+        if (root) {
+            for (int peer = 1; peer < world; ++peer) {
+                size_t const peer_rows = (size_t)(communicator.bounds[peer + 1] - communicator.bounds[peer]);
+                if (peer_rows)
+                    SZB_NCCL(nccl.Recv(slab + (size_t)communicator.bounds[peer] * columns, peer_rows * columns * sizeof(int64_t),
+                                       ncclUint8, peer, communicator.comm, stream));
+            }
+        }
+        else if (end > begin)
+            SZB_NCCL(nccl.Send(slab, (end - begin) * columns * sizeof(int64_t), ncclUint8, 0, communicator.comm, stream));
+        SZB_NCCL(nccl.GroupEnd());
+    }
+    if (root && n_q && columns) {
+        if (!results) return fail(sz_unexpected_dimensions_k, "Results pointer is null");
+        if (stride < columns) return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
+        if (symmetric && world > 1 && n_q > 1) {
+            int const sms = std::max(1, device_facts(scope.gpu_device).sms);
+            mirror_lower_kernel<<<helper_grid(n_q * n_q, 256, sms, 16), 256, 0, stream>>>(slab, n_q, columns);
+            SZB_CUDA(cudaGetLastError());
+        }
+        SZB_CUDA(cudaMemcpy2DAsync(results, stride * sizeof(int64_t), slab, columns * sizeof(int64_t), columns * sizeof(int64_t),
+                                   (size_t)n_q, cudaMemcpyDefault, stream));
+    }
+    SZB_CUDA(cudaStreamSynchronize(stream));
+    return ok();
+}
+
+} // namespace szb
+
+#pragma endregion
+
 #pragma region C ABI
 
 using szb::Engine;
@@ -1480,7 +2042,8 @@ SZS_B200_API sz_capability_t szs_capabilities_comptime(void) {
 SZS_B200_API sz_capability_t szs_capabilities_runtime(void) {
     // Like the reference (runtime.cuh:27-45): an unreachable GPU contributes no bits instead of an error.
     int caps = sz_cap_serial_k;
-    if (szb::visible_device_count() > 0 && szb::device_sm_code(0) >= 100) caps |= sz_caps_cuda_k;
+    for (int device = 0, count = szb::visible_device_count(); device < count; ++device)
+        if (szb::device_sm_code(device) >= 100) caps |= sz_caps_cuda_k;
     return (sz_capability_t)caps;
 }
 
@@ -1750,8 +2313,8 @@ SZS_B200_API sz_status_t szs_b200_debug_schedule(void const *engine_punned, sz_u
     szb::build_model(engine, present, false, model);
     szb::Schedule schedule;
     szb::Trace const trace;
-    szb::Failure failure = szb::build_schedule(engine, model, qs, cs, symmetric, true, 0, qs.count, present, false,
-                                               std::max(device_sms, 1), trace, schedule);
+    szb::Failure failure = szb::build_schedule(engine, model, qs, cs, symmetric, true, 0, qs.count, cs.count, present,
+                                               false, std::max(device_sms, 1), trace, schedule);
     if (failure) return failure.status;
     for (size_t c = 0; c < cs.count; ++c) assignment[c] = 0xFFFFFFFFu, partner[c] = 0xFFFFFFFFu;
     for (szb::MyersLaunch const &launch : schedule.myers_launches)
@@ -1794,6 +2357,107 @@ SZS_B200_API sz_status_t szs_b200_scores_u64tape_rows(int family, void *engine, 
     Failure failure = szb::cross(*typed, *static_cast<Scope *>(device), q, c, results, results_row_stride, row_begin,
                                  row_end, false);
     return szb::report(failure, error_message);
+}
+
+SZS_B200_API sz_status_t szs_b200_partition_rows(sz_u64_t const *lengths, sz_size_t count, sz_size_t parts, int symmetric,
+                                                 sz_u64_t *bounds) {
+    if ((!lengths && count) || !bounds || !parts) return sz_status_unknown_k;
+    szb::partition_rows(lengths, count, parts, symmetric != 0, bounds);
+    return sz_success_k;
+}
+
+SZS_B200_API sz_status_t szs_b200_device_group_init(sz_size_t const *gpu_devices, sz_size_t count,
+                                                    szs_b200_device_group_t *group, char const **error_message) {
+    if (!group) return szb::report(szb::fail(sz_status_unknown_k, "Group pointer is null"), error_message);
+    size_t const visible = (size_t)szb::visible_device_count();
+    if (!gpu_devices) count = visible; // every visible device
+    if (!count) return szb::report(szb::fail(sz_missing_gpu_k, "No CUDA device is visible"), error_message);
+    std::unique_ptr<szb::DeviceGroup> made(new (std::nothrow) szb::DeviceGroup());
+    if (!made) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate the device group"), error_message);
+    for (size_t i = 0; i < count; ++i) {
+        size_t const device = gpu_devices ? gpu_devices[i] : i;
+        if (device >= visible) return szb::report(szb::fail(sz_missing_gpu_k, "No such CUDA device"), error_message);
+        std::unique_ptr<Scope> scope(new (std::nothrow) Scope());
+        if (!scope) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate device scope"), error_message);
+        scope->kind = Scope::kGpu, scope->cpu_cores = 0, scope->gpu_device = (int)device;
+        made->scopes.push_back(std::move(scope));
+    }
+    made->start();
+    *group = made.release();
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_b200_device_group_size(szs_b200_device_group_t group, sz_size_t *count) {
+    if (!group || !count) return sz_status_unknown_k;
+    *count = static_cast<szb::DeviceGroup *>(group)->scopes.size();
+    return sz_success_k;
+}
+
+SZS_B200_API void szs_b200_device_group_free(szs_b200_device_group_t group) {
+    delete static_cast<szb::DeviceGroup *>(group);
+}
+
+SZS_B200_API sz_status_t szs_b200_scores_u64tape_sharded(int family, void *engine, szs_b200_device_group_t group,
+                                                         sz_sequence_u64tape_t const *queries,
+                                                         sz_sequence_u64tape_t const *candidates, void *results,
+                                                         sz_size_t results_row_stride, char const **error_message) {
+    if (!engine || !group || !queries)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine, device group and queries must not be null"), error_message);
+    auto *typed = static_cast<Engine *>(engine);
+    if ((int)typed->algorithm != family)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine handle belongs to another algorithm"), error_message);
+    return szb::report(szb::sharded_cross(*typed, *static_cast<szb::DeviceGroup *>(group), queries, candidates, results,
+                                          results_row_stride),
+                       error_message);
+}
+
+SZS_B200_API sz_status_t szs_b200_comm_unique_id(void *unique_id, char const **error_message) {
+    if (!unique_id) return szb::report(szb::fail(sz_status_unknown_k, "Identifier pointer is null"), error_message);
+    szb::NcclApi const &nccl = szb::nccl_api();
+    if (!nccl.ready()) return szb::report(szb::fail(sz_status_unknown_k, "libnccl.so.2 could not be loaded"), error_message);
+    static_assert(sizeof(ncclUniqueId) == SZS_B200_COMM_ID_BYTES, "identifier size is part of the ABI");
+    ncclResult_t const result = nccl.GetUniqueId(static_cast<ncclUniqueId *>(unique_id));
+    if (result != ncclSuccess) return szb::report(szb::fail(sz_status_unknown_k, nccl.GetErrorString(result)), error_message);
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API sz_status_t szs_b200_comm_init(void const *unique_id, int world_size, int rank, sz_size_t gpu_device,
+                                            szs_b200_comm_t *comm, char const **error_message) {
+    if (!unique_id || !comm || world_size < 1 || rank < 0 || rank >= world_size)
+        return szb::report(szb::fail(sz_status_unknown_k, "Invalid communicator arguments"), error_message);
+    szb::NcclApi const &nccl = szb::nccl_api();
+    if (!nccl.ready()) return szb::report(szb::fail(sz_status_unknown_k, "libnccl.so.2 could not be loaded"), error_message);
+    if ((size_t)szb::visible_device_count() <= gpu_device)
+        return szb::report(szb::fail(sz_missing_gpu_k, "No such CUDA device"), error_message);
+    std::unique_ptr<szb::Communicator> made(new (std::nothrow) szb::Communicator());
+    if (!made) return szb::report(szb::fail(sz_bad_alloc_k, "Failed to allocate the communicator"), error_message);
+    made->world = world_size, made->rank = rank, made->device = (int)gpu_device;
+    if (cudaSetDevice((int)gpu_device) != cudaSuccess) {
+        cudaGetLastError();
+        return szb::report(szb::fail(sz_missing_gpu_k, "cudaSetDevice failed"), error_message);
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    ncclResult_t const result = nccl.CommInitRank(&made->comm, world_size, id, rank);
+    if (result != ncclSuccess) return szb::report(szb::fail(sz_status_unknown_k, nccl.GetErrorString(result)), error_message);
+    *comm = made.release();
+    return szb::report(szb::ok(), error_message);
+}
+
+SZS_B200_API void szs_b200_comm_free(szs_b200_comm_t comm) { delete static_cast<szb::Communicator *>(comm); }
+
+SZS_B200_API sz_status_t szs_b200_comm_scores_u64tape(int family, void *engine, szs_device_scope_t device,
+                                                      szs_b200_comm_t comm, sz_sequence_u64tape_t const *queries,
+                                                      sz_sequence_u64tape_t const *candidates, void *results,
+                                                      sz_size_t results_row_stride, char const **error_message) {
+    if (!engine || !device || !comm)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine, device scope and communicator must not be null"), error_message);
+    auto *typed = static_cast<Engine *>(engine);
+    if ((int)typed->algorithm != family)
+        return szb::report(szb::fail(sz_status_unknown_k, "Engine handle belongs to another algorithm"), error_message);
+    return szb::report(szb::communicator_cross(*typed, *static_cast<Scope *>(device), *static_cast<szb::Communicator *>(comm),
+                                               queries, candidates, results, results_row_stride),
+                       error_message);
 }
 
 } // extern "C"

@@ -4,6 +4,8 @@
  */
 #include "launch.cuh"
 
+#include <atomic>
+
 #ifndef SZB_FAMILY
 #error "compile with -DSZB_FAMILY=<family index>"
 #endif
@@ -14,13 +16,16 @@ template <int FAM, int STRIP>
 static cudaError_t launch_strip(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
     auto kernel = wavefront_kernel<FAM, kStrips[STRIP]>;
     // Opt in to the large dynamic shared-memory carve-out once per kernel and device.
-    static bool configured[64] = {false};
+    // Engines on different host threads launch concurrently: one atomic bit per device; devices past the mask are
+    // configured on every launch.
+    static std::atomic<uint64_t> configured {0};
     int device = 0;
     cudaGetDevice(&device);
-    if (device < 64 && !configured[device]) {
+    uint64_t const bit = device < 64 ? 1ull << device : 0;
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         cudaError_t status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (status != cudaSuccess) return status;
-        configured[device] = true;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     kernel<<<grid, kThreads, smem, stream>>>(args);
     return cudaGetLastError();

@@ -22,9 +22,10 @@ struct Shape {
 /**
  *  Picks the (K, G) whose coverage K * G fits `longest` columns most tightly: the cost of sweeping a query over a
  *  slot is proportional to the coverage, not to the candidate's length. Ties go to the wider strip (less per-step
- *  overhead). Candidates longer than the widest shape are split into equal passes.
+ *  overhead). Candidates longer than the widest shape are split into equal passes. `min_lanes` = 32 serves calls too
+ *  small to fill the device: the widest wavefront has the shortest dependent chain per step.
  */
-inline Shape shape_for_length(uint32_t longest) {
+inline Shape shape_for_length(uint32_t longest, int min_lanes = 8) {
     Shape best = {kStripCount - 1, 32};
     if (longest > (uint32_t)kMaxCoverage) {
         uint32_t const passes = (longest + kMaxCoverage - 1) / kMaxCoverage;
@@ -34,7 +35,7 @@ inline Shape shape_for_length(uint32_t longest) {
         return best;
     }
     int best_coverage = kMaxCoverage + 1;
-    for (int lanes = 8; lanes <= 32; lanes *= 2)
+    for (int lanes = min_lanes; lanes <= 32; lanes *= 2)
         for (int i = 0; i < kStripCount; ++i) {
             int const coverage = kStrips[i] * lanes;
             if ((uint32_t)coverage < longest) continue;

@@ -4,18 +4,23 @@
  */
 #include "myers.cuh"
 
+#include <atomic>
+
 namespace szb {
 
 template <int W, bool SHARED>
 static cudaError_t launch_words(int grid, int threads, size_t smem, cudaStream_t stream, MyersArgs const &args) {
     auto kernel = SHARED ? myers_shared_kernel<W> : myers_kernel<W>;
-    static bool configured[64] = {false};
+    // Engines on different host threads launch concurrently: one atomic bit per device; devices past the mask are
+    // configured on every launch.
+    static std::atomic<uint64_t> configured {0};
     int device = 0;
     cudaGetDevice(&device);
-    if (device < 64 && !configured[device]) {
+    uint64_t const bit = device < 64 ? 1ull << device : 0;
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         cudaError_t status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (status != cudaSuccess) return status;
-        configured[device] = true;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     kernel<<<grid, threads, smem, stream>>>(args);
     return cudaGetLastError();
