@@ -33,6 +33,9 @@ static cudaError_t launch_strip(int grid, size_t smem, cudaStream_t stream, Kern
 
 template <>
 cudaError_t launch_family<SZB_FAMILY>(int strip, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
+#ifdef SZB_ONLY_STRIP // kernel experiments: instantiate a single strip width (tools/sass_mix.py)
+    return launch_strip<SZB_FAMILY, SZB_ONLY_STRIP>(grid, smem, stream, args);
+#endif
     switch (strip) {
     case 0: return launch_strip<SZB_FAMILY, 0>(grid, smem, stream, args);
     case 1: return launch_strip<SZB_FAMILY, 1>(grid, smem, stream, args);

@@ -129,8 +129,18 @@ __device__ __forceinline__ int profile_term(int8_t const *sub, int a, int b, boo
     int const s = valid ? (int)sub[a * 32 + b] : 0;
     if constexpr (family_traits<FAM>::linear_shift) { return valid ? max(s - 2 * open, 0) : 0; }
     else if constexpr (FAM == FAM_AFF_SHIFT) { return valid ? max(s, 2 * open) - 2 * extend : 2 * (open - extend); }
-    else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) { return valid ? s : -bias; }
+    else if constexpr (FAM == FAM_SW_LIN) { return valid ? s : -bias; }
+    else if constexpr (FAM == FAM_SW_AFF) { return valid ? s - open : -open - bias; } // cells are kept as H + open
     else { return valid ? s : -(1 << 28); }
+}
+
+/** A 32-bit add that is guaranteed to issue on the FMA pipe (IMAD with a multiplier the compiler cannot fold): the
+ *  packed recurrences saturate the ALU pipe with DPX instructions, and ptxas otherwise turns part of the plain adds
+ *  into ALU-pipe VIADDs. */
+__device__ __forceinline__ uint32_t add_on_fma_pipe(uint32_t a, uint32_t b, uint32_t one) {
+    uint32_t sum;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(a), "r"(one), "r"(b));
+    return sum;
 }
 
 /** Score of aligning `len` characters against nothing: serial.hpp:165-177 of the reference. */
@@ -153,6 +163,9 @@ struct SweepConstants {
     uint32_t ext_arith;    // FAM_SW_AFF: "+ extend" through a plain add
     uint32_t cmp_match_bits; // FAM_LIN_SHIFT compare mode: e(match) in both halves
     uint32_t cmp_drop_bits;  // FAM_LIN_SHIFT compare mode: e(match) - e(mismatch) >= 0 in both halves
+    uint32_t ext_bits;       // FAM_SW_AFF: "+ extend" for VIADDMNMX
+    uint32_t open_arith;     // FAM_SW_AFF: "+ open" through a plain add
+    uint32_t one;            // the opaque multiplier of add_on_fma_pipe
 };
 
 /**
@@ -228,16 +241,21 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         diag_in = first_strip ? pack_bits(bias) : top;
         left_boundary = top, left_gap_boundary = 0;
     }
-    else if constexpr (FAM == FAM_SW_LIN || FAM == FAM_SW_AFF) {
+    else if constexpr (FAM == FAM_SW_LIN) {
 #pragma unroll
         for (int k = 0; k < K; ++k) h[k] = sc.bias_bits;
-        if constexpr (affine) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) f[k] = pack_bits(bias + open + extend);
-        }
         diag_in = sc.bias_bits;
         best = sc.bias_bits;
-        left_boundary = sc.bias_bits, left_gap_boundary = pack_bits(bias + open + extend);
+        left_boundary = sc.bias_bits;
+    }
+    else if constexpr (FAM == FAM_SW_AFF) {
+        // Cells are kept as H + open (what both gap tracks consume); the vertical track is kept floored at zero.
+        uint32_t const zero_cell = pack_bits(bias + open);
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = zero_cell, f[k] = sc.bias_bits;
+        diag_in = zero_cell;
+        best = zero_cell;
+        left_boundary = zero_cell, left_gap_boundary = pack_bits(bias + open + extend);
     }
     else {
 #pragma unroll
@@ -308,9 +326,30 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         }
 
         if (valid) {
-            uint32_t d = diag_in, l = w_in, e = e_in;
+            uint32_t l = w_in, e = e_in;
             uint32_t const row_address = strip_address + a * row_bytes;
             uint32_t const a_twice = a * 0x01000100u; // compare mode of the packed family: the row byte in both halves
+            // Compare modes form the substitution term of strip column k from the strip's symbols in registers.
+            auto compared = [&](int k) -> uint32_t {
+                if constexpr (FAM == FAM_LIN_COMPARE) return sc.cmp_match_bits - __vminu2(cb[k] ^ a_twice, sc.cmp_drop_bits);
+                else if constexpr (!packed) return (uint32_t)(cb[k] == a ? sc.cmp_match : sc.cmp_mismatch);
+                else return 0u;
+            };
+            auto add = [&](uint32_t x, uint32_t y) -> uint32_t {
+                if constexpr (packed) return add_on_fma_pipe(x, y, sc.one);
+                else return x + y;
+            };
+            // Profile rows are stored ROTATED by one column: vector v of a strip holds the terms of its columns
+            // 4v+1 .. 4v+4, the last slot of the last vector the term of column 0. The diagonal sums of those columns
+            // are formed from the previous row's cells the moment the vector arrives — before any of them is
+            // overwritten — so every cell of the strip is updated in place and nothing has to be moved aside.
+            uint32_t t_carry;
+            if (!compare) {
+                uint32_t first;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(first) : "r"(row_address + (uint32_t)(VECS - 1) * 512u + 12u));
+                t_carry = add(diag_in, first);
+            }
+            else { t_carry = add(diag_in, compared(0)); }
 #pragma unroll
             for (int v = 0; v < VECS; ++v) {
                 uint32_t p[4];
@@ -320,55 +359,46 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                                  : "r"(row_address + (uint32_t)v * 512u));
                 }
                 else {
-                    if constexpr (!packed) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            p[i] = (uint32_t)(cb[v * 4 + i] == a ? sc.cmp_match : sc.cmp_mismatch);
-                    }
-                    else if constexpr (FAM == FAM_LIN_COMPARE) {
-                        // e = e(match) - min(byte XOR, drop): the XOR is 0 on a match and >= 255 >= drop otherwise.
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            p[i] = sc.cmp_match_bits - __vminu2(cb[v * 4 + i] ^ a_twice, sc.cmp_drop_bits);
-                    }
+                    for (int i = 0; i < 4; ++i) p[i] = compared((v * 4 + 1 + i) % K);
                 }
-                // The four diagonal terms of this vector depend only on the previous row: form them before the
-                // cells of the current row overwrite the strip.
-                uint32_t t4[4];
-                t4[0] = d + p[0], t4[1] = h[v * 4] + p[1], t4[2] = h[v * 4 + 1] + p[2], t4[3] = h[v * 4 + 2] + p[3];
-                d = h[v * 4 + 3];
+                uint32_t t_next[4]; // diagonal sums of columns 4v+1 .. 4v+4 (the last one of the strip is not needed)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) t_next[i] = add(h[v * 4 + i], p[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     int const k = v * 4 + i;
-                    if constexpr (traits::linear_shift) { l = h[k] = __vimax3_u16x2(t4[i], h[k], l); }
+                    uint32_t const t = i == 0 ? t_carry : t_next[i - 1];
+                    if constexpr (traits::linear_shift) { l = h[k] = __vimax3_u16x2(t, h[k], l); }
                     else if constexpr (FAM == FAM_AFF_SHIFT) {
                         f[k] = __viaddmax_u16x2(h[k], sc.neg_go_bits, f[k]);
                         e = __viaddmax_u16x2(l, sc.neg_go_bits, e);
-                        l = h[k] = __vimax3_u16x2(t4[i], f[k], e);
+                        l = h[k] = __vimax3_u16x2(t, f[k], e);
                     }
                     else if constexpr (FAM == FAM_SW_LIN) {
-                        uint32_t const up_gap = h[k] + sc.gap_arith;
-                        uint32_t const x = __vimax3_u16x2(t4[i], up_gap, sc.bias_bits);
+                        uint32_t const up_gap = add(h[k], sc.gap_arith);
+                        uint32_t const x = __vimax3_u16x2(t, up_gap, sc.bias_bits);
                         l = h[k] = __viaddmax_u16x2(l, sc.gap_bits, x);
                         if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
                     }
                     else if constexpr (FAM == FAM_SW_AFF) {
-                        f[k] = __viaddmax_u16x2(h[k], sc.gap_bits, f[k] + sc.ext_arith);
-                        e = __viaddmax_u16x2(l, sc.gap_bits, e + sc.ext_arith);
-                        uint32_t const x = __vimax3_u16x2(t4[i], f[k], sc.bias_bits);
-                        l = h[k] = __vmaxu2(x, e);
+                        // h[] holds H + open. The vertical track is floored at zero (exact: H is floored anyway and
+                        // extend <= 0), which leaves ONE three-way maximum for the cell: 3 DPX + 3 FMA-pipe adds.
+                        f[k] = __vimax3_u16x2(h[k], add(f[k], sc.ext_arith), sc.bias_bits);
+                        e = __viaddmax_u16x2(e, sc.ext_bits, l);
+                        l = h[k] = add(__vimax3_u16x2(t, e, f[k]), sc.open_arith);
                         if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
                     }
                     else { // signed 32-bit cells, literal recurrences
-                        int const t = (int)t4[i];
+                        int const ti = (int)t;
                         int score;
                         if constexpr (affine) {
                             int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
                             int const ins = __viaddmax_s32((int)l, open, (int)e + extend);
                             f[k] = (uint32_t)del, e = (uint32_t)ins;
-                            score = __vimax3_s32(t, del, ins);
+                            score = __vimax3_s32(ti, del, ins);
                         }
-                        else { score = __viaddmax_s32(max((int)h[k], (int)l), open, t); }
+                        else { score = __viaddmax_s32(max((int)h[k], (int)l), open, ti); }
                         if constexpr (local) {
                             score = max(score, 0);
                             // Gap rewards can inflate padding columns: only real cells compete.
@@ -377,6 +407,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                         l = h[k] = (uint32_t)score;
                     }
                 }
+                t_carry = t_next[3];
             }
             diag_in = w_in;
             w_out = l, e_out = e;
@@ -430,7 +461,8 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                 if constexpr (packed) group_best = __vmaxu2(group_best, other);
                 else group_best = (uint32_t)max((int)group_best, (int)other);
             }
-            int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias : (int64_t)(int)group_best;
+            int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias - (FAM == FAM_SW_AFF ? open : 0)
+                                   : (int64_t)(int)group_best;
             if (gl == 0 && q_valid) {
                 // Later passes of a long candidate fold into the cell written by pass 0 (same CTA, ordered by
                 // the pass barrier).
@@ -470,6 +502,8 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     }
     sc.neg_go_bits = pack_bits(-sc.go), sc.bias_bits = pack_bits(sc.bias), sc.gap_bits = pack_bits(sc.open);
     sc.gap_arith = pack_arith(sc.open, sc.open), sc.ext_arith = pack_arith(sc.extend, sc.extend);
+    sc.ext_bits = pack_bits(sc.extend), sc.open_arith = pack_arith(sc.open, sc.open);
+    sc.one = blockDim.x / kThreads; // 1, but not a constant ptxas can fold: the adds stay IMADs
 
     for (int i = threadIdx.x; i < 256; i += kThreads) ((uint32_t *)sub)[i] = ((uint32_t const *)sc_global->sub)[i];
     int const lane = threadIdx.x & 31;
@@ -505,10 +539,11 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
                     int const b0 = v0 ? c0_ptr[col] : 0, b1 = v1 ? c1_ptr[col] : 0;
                     int const e0 = profile_term<FAM>(sub, a, b0, v0, sc.open, sc.extend, sc.bias);
                     int const e1 = profile_term<FAM>(sub, a, b1, v1, sc.open, sc.extend, sc.bias);
-                    // Row layout: [vector v = k / 4][strip slot, 32 per vector][4 words]; a strip is one lane's K
-                    // columns, so lane `gl` reads its v-th vector at the compile-time offset v * 512 bytes.
+                    // Row layout: [vector][strip slot, 32 per vector][4 words]; a strip is one lane's K columns, so lane
+                    // `gl` reads its v-th vector at the compile-time offset v * 512 bytes.
                     int const strip = j / K, k = j - strip * K;
-                    int const word = ((k / 4) * 32 + strip) * 4 + (k % 4);
+                    int const rotated = k == 0 ? K - 1 : k - 1; // column k's term sits one slot early (see sweep_batch)
+                    int const word = ((rotated / 4) * 32 + strip) * 4 + (rotated % 4);
                     prof[a * (K * 32) + word] = packed ? pack_arith(e0, e1) : (uint32_t)e0;
                 }
             }
