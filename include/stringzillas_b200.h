@@ -300,6 +300,10 @@ typedef struct szs_b200_call_stats_t {
 } szs_b200_call_stats_t;
 SZS_B200_API sz_status_t szs_b200_last_call_stats(void const *engine, szs_b200_call_stats_t *stats);
 
+/** The CUDA stream (`cudaStream_t`) every call on this GPU scope enqueues its work on — one stream per scope, like
+ *  the reference's `cuda_executor_t` (types.cuh:403-473). Lets a caller bracket calls with its own CUDA events. */
+SZS_B200_API sz_status_t szs_b200_device_scope_stream(szs_device_scope_t scope, void **stream, char const **error_message);
+
 /** Unit-cost byte-level Levenshtein normally runs the bit-parallel (Myers/Hyyro) kernel, as every reference backend
  *  does (serial.hpp:2636-2642); `enabled = 0` keeps such engines on the int16 DPX wavefront tier (used by bench.py to
  *  measure that tier on the headline workload). Results are identical either way. */

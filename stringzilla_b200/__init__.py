@@ -133,6 +133,13 @@ class DeviceScope:
         return self._handle
 
     @property
+    def stream(self) -> int:
+        """The `cudaStream_t` (as an integer) every call on this GPU scope enqueues its work on."""
+        value, message = ct.c_void_p(), ct.c_char_p()
+        _abi.check(self._lib.szs_b200_device_scope_stream(self._handle, ct.byref(value), ct.byref(message)), message)
+        return int(value.value or 0)
+
+    @property
     def cpu_cores(self) -> int:
         value, message = ct.c_uint64(), ct.c_char_p()
         _abi.check(self._lib.szs_device_scope_get_cpu_cores(self._handle, ct.byref(value), ct.byref(message)), message)

@@ -113,7 +113,7 @@ REFERENCE_SYMBOLS = [
     "szs_fingerprints_free",
 ]  # fmt: skip
 B200_SYMBOLS = ["szs_b200_last_call_stats", "szs_b200_scores_u64tape_rows", "szs_b200_set_bit_parallel",
-                "szs_b200_debug_schedule", "szs_b200_partition_rows", "szs_b200_device_group_init",
+                "szs_b200_debug_schedule", "szs_b200_device_scope_stream", "szs_b200_partition_rows", "szs_b200_device_group_init",
                 "szs_b200_device_group_size", "szs_b200_device_group_free", "szs_b200_scores_u64tape_sharded",
                 "szs_b200_comm_unique_id", "szs_b200_comm_init", "szs_b200_comm_free", "szs_b200_comm_scores_u64tape"]
 COMM_ID_BYTES = 128
@@ -172,6 +172,8 @@ def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
         lib.szs_b200_set_bit_parallel.restype = ct.c_int
         lib.szs_b200_debug_schedule.argtypes = [vp, vp, u64, vp, u64, ct.c_int, ct.c_int, vp, vp, vp, vp, u64, ct.POINTER(u64)]
         lib.szs_b200_debug_schedule.restype = ct.c_int
+        lib.szs_b200_device_scope_stream.argtypes = [vp, ct.POINTER(vp), err]
+        lib.szs_b200_device_scope_stream.restype = ct.c_int
         lib.szs_b200_partition_rows.argtypes = [vp, u64, u64, ct.c_int, vp]
         lib.szs_b200_partition_rows.restype = ct.c_int
         lib.szs_b200_device_group_init.argtypes = [vp, u64, ct.POINTER(vp), err]

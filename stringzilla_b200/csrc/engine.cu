@@ -2337,6 +2337,15 @@ SZS_B200_API sz_status_t szs_b200_debug_schedule(void const *engine_punned, sz_u
     return sz_success_k;
 }
 
+SZS_B200_API sz_status_t szs_b200_device_scope_stream(szs_device_scope_t scope, void **stream, char const **error_message) {
+    if (!scope || !stream) return szb::report(szb::fail(sz_status_unknown_k, "Invalid null pointer argument"), error_message);
+    auto *typed = static_cast<Scope *>(scope);
+    if (typed->kind == Scope::kCpu) return szb::report(szb::fail(sz_device_code_mismatch_k, "Device scope is CPU-only"), error_message);
+    if (Failure failure = typed->ensure_stream()) return szb::report(failure, error_message);
+    *stream = typed->stream;
+    return szb::report(szb::ok(), error_message);
+}
+
 SZS_B200_API sz_status_t szs_b200_set_bit_parallel(void *engine, int enabled) {
     if (!engine) return sz_status_unknown_k;
     static_cast<Engine *>(engine)->bit_parallel = enabled != 0;

@@ -29,6 +29,9 @@ static cudaError_t launch_words(int grid, int threads, size_t smem, cudaStream_t
 template <bool SHARED>
 static cudaError_t launch_variant(int words, int grid, int threads, size_t smem, cudaStream_t stream,
                                   MyersArgs const &args) {
+#ifdef SZB_ONLY_WORDS // kernel experiments: instantiate a single word count (tools/sass_mix.py)
+    return launch_words<SZB_ONLY_WORDS, SHARED>(grid, threads, smem, stream, args);
+#endif
     switch (words) {
     case 1: return launch_words<1, SHARED>(grid, threads, smem, stream, args);
     case 2: return launch_words<2, SHARED>(grid, threads, smem, stream, args);

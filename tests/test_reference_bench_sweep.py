@@ -111,3 +111,27 @@ def test_b200_library_against_the_reference_cpu_baseline(tmp_path):
     dataset, expected = known_answers(tmp_path)
     out = run_benchmark(SZS_BASELINE_LIB="none", STRINGWARS_STRESS="0", STRINGWARS_DATASET=str(dataset), STRINGWARS_BATCH="6")
     check_known_answers(out, expected, "b200")
+
+
+@pytest.mark.gpu
+def test_reference_benchmark_runs_the_b200_engines(tmp_path):
+    """the REFERENCE's own benchmark binary (bench/similarities.cu compiled from /root/reference by
+    oracle/build_ref_bench.sh, with this library's engines registered through bench/reference_bench_b200.cuh) runs its
+    serial-vs-accelerated equality check (bench/similarities.cuh:410-423) over every `*_b200*` engine."""
+    binary = ROOT / "oracle" / "_ref" / "ref_bench_similarities"
+    if not binary.exists():
+        pytest.skip("oracle/_ref/ref_bench_similarities is not built (needs /root/reference at build time)")
+    dataset = tmp_path / "proteins.txt"
+    subprocess.run(["python", str(ROOT / "tools" / "make_dataset.py"), str(dataset), "900", "90", "160", "protein"], check=True)
+    env = dict(os.environ, STRINGWARS_DATASET=str(dataset), STRINGWARS_TOKENS="lines", STRINGWARS_DURATION="1",
+               STRINGWARS_STRESS="1", STRINGWARS_STRESS_DURATION="1", STRINGWARS_STRESS_DIR=str(tmp_path),
+               STRINGWARS_FILTER="_b200", STRINGWARS_BATCH="24")
+    done = subprocess.run([str(binary)], env=env, capture_output=True, text=True, timeout=900)
+    out = done.stdout + done.stderr
+    assert done.returncode == 0, out[-3000:]
+    assert "All benchmarks finished." in out and "Mismatch" not in out and "> Errors" not in out, out[-3000:]
+    names = re.findall(r"Benchmarking `([^`]+)`", out)
+    for expected in ("levenshtein_b200_unit", "affine_levenshtein_b200_weird", "needleman_wunsch_b200", "smith_waterman_b200",
+                     "affine_needleman_wunsch_b200", "affine_smith_waterman_b200"):
+        assert any(name.startswith(expected + ":") for name in names), (expected, names)
+    assert out.count("> Kernel:") >= len([n for n in names if "_b200" in n])  # device time reported through cuda_status_t
