@@ -143,6 +143,34 @@ __device__ __forceinline__ uint32_t add_on_fma_pipe(uint32_t a, uint32_t b, uint
     return sum;
 }
 
+/* ---- TMA (bulk asynchronous copy) of the slot's candidate bytes into shared memory, completion on an mbarrier ------ */
+
+/** Bytes reserved per staged candidate window: the widest pass (40 x 32 columns) plus the 16-byte alignment slack at
+ *  both ends. */
+constexpr int kStageBytes = 40 * 32 + 32;
+
+__device__ __forceinline__ void mbarrier_init(uint32_t barrier, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbarrier_expect_bytes(uint32_t barrier, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "r"(bytes) : "memory");
+}
+/** One 1-D bulk copy global -> shared (`cp.async.bulk`, the TMA engine without a tensor map: these are byte runs).
+ *  Source, destination and size are multiples of 16 bytes. */
+__device__ __forceinline__ void bulk_copy_to_shared(uint32_t destination, void const *source, uint32_t bytes, uint32_t barrier) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(destination),
+                 "l"(source), "r"(bytes), "r"(barrier)
+                 : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint32_t barrier, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred arrived;\n\t"
+                 "SZB_WAIT_FOR_BYTES:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 arrived, [%0], %1;\n\t"
+                 "@!arrived bra SZB_WAIT_FOR_BYTES;\n\t}" ::"r"(barrier),
+                 "r"(parity)
+                 : "memory");
+}
+
 /** Score of aligning `len` characters against nothing: serial.hpp:165-177 of the reference. */
 template <int FAM>
 __device__ __forceinline__ int64_t degenerate_score(int64_t len, int open, int extend) {
@@ -487,9 +515,13 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     extern __shared__ __align__(16) uint32_t smem[];
     Scoring const *const sc_global = args.scoring;
     int const n_classes = sc_global->n_classes;
-    uint32_t *const ctl = smem;                // [0] job index, [1] next batch
+    uint32_t *const ctl = smem;                // [0] job index, [1] next batch, [2..3] the mbarrier of the TMA copies
     int8_t *const sub = (int8_t *)(smem + 4);  // 1024 B
-    uint32_t *const prof = smem + 4 + 256;     // [n_classes][K / 4][32 slots][4]; unused in compare mode
+    uint8_t *const stage = (uint8_t *)(smem + 4 + 256); // 2 x kStageBytes: the slot's candidate bytes of this pass
+    uint32_t *const prof = smem + 4 + 256 + 2 * kStageBytes / 4; // [n_classes][K / 4][32 slots][4]; unused in compare mode
+    uint32_t const barrier = (uint32_t)__cvta_generic_to_shared(ctl + 2);
+    uint32_t const stage_address = (uint32_t)__cvta_generic_to_shared(stage);
+    uint32_t barrier_parity = 0;
 
     SweepConstants sc;
     sc.open = sc_global->open, sc.extend = sc_global->extend, sc.bias = sc_global->bias;
@@ -506,6 +538,10 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     sc.one = blockDim.x / kThreads; // 1, but not a constant ptxas can fold: the adds stay IMADs
 
     for (int i = threadIdx.x; i < 256; i += kThreads) ((uint32_t *)sub)[i] = ((uint32_t const *)sc_global->sub)[i];
+    if (threadIdx.x == 0) {
+        mbarrier_init(barrier, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     int const lane = threadIdx.x & 31;
 
     for (;;) {
@@ -530,13 +566,30 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
             __syncthreads(); // every warp is done with the previous profile and batch counter
             if (threadIdx.x == 0) ctl[1] = 0;
 
-            // 1. Build the substitution profile of this slot's columns [pass_base, pass_base + COLS).
+            // 1. Build the substitution profile of this slot's columns [pass_base, pass_base + COLS). The candidate bytes
+            //    of the pass arrive through the TMA engine: one thread arms the mbarrier with the byte count and issues
+            //    one bulk copy per candidate (16-byte aligned windows around the columns), everybody waits on the barrier.
             if (!sc.compare) {
+                uint32_t const columns0 = slot.len0 > pass_base ? min((uint32_t)COLS, slot.len0 - pass_base) : 0;
+                uint32_t const columns1 = slot.len1 > pass_base ? min((uint32_t)COLS, slot.len1 - pass_base) : 0;
+                uint8_t const *const begin0 = c0_ptr + pass_base, *const begin1 = c1_ptr + pass_base;
+                uint32_t const skew0 = (uint32_t)((uintptr_t)begin0 & 15), skew1 = (uint32_t)((uintptr_t)begin1 & 15);
+                uint32_t const bytes0 = columns0 ? (skew0 + columns0 + 15) & ~15u : 0;
+                uint32_t const bytes1 = columns1 ? (skew1 + columns1 + 15) & ~15u : 0;
+                if (bytes0 + bytes1) { // uniform across the CTA
+                    if (threadIdx.x == 0) {
+                        mbarrier_expect_bytes(barrier, bytes0 + bytes1);
+                        if (bytes0) bulk_copy_to_shared(stage_address, begin0 - skew0, bytes0, barrier);
+                        if (bytes1) bulk_copy_to_shared(stage_address + kStageBytes, begin1 - skew1, bytes1, barrier);
+                    }
+                    mbarrier_wait(barrier, barrier_parity);
+                    barrier_parity ^= 1;
+                }
+                uint8_t const *const staged0 = stage + skew0, *const staged1 = stage + kStageBytes + skew1;
                 for (int idx = threadIdx.x; idx < n_classes * COLS; idx += kThreads) {
                     int const a = idx / COLS, j = idx - a * COLS;
-                    uint32_t const col = pass_base + j;
-                    bool const v0 = col < slot.len0, v1 = col < slot.len1;
-                    int const b0 = v0 ? c0_ptr[col] : 0, b1 = v1 ? c1_ptr[col] : 0;
+                    bool const v0 = (uint32_t)j < columns0, v1 = (uint32_t)j < columns1;
+                    int const b0 = v0 ? staged0[j] : 0, b1 = v1 ? staged1[j] : 0;
                     int const e0 = profile_term<FAM>(sub, a, b0, v0, sc.open, sc.extend, sc.bias);
                     int const e1 = profile_term<FAM>(sub, a, b1, v1, sc.open, sc.extend, sc.bias);
                     // Row layout: [vector][strip slot, 32 per vector][4 words]; a strip is one lane's K columns, so lane

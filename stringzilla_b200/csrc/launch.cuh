@@ -45,11 +45,11 @@ inline Shape shape_for_length(uint32_t longest, int min_lanes = 8) {
     return best;
 }
 
-/** Dynamic shared memory of one CTA: two control words, the 32x32 table, and the profile: per class K / 4 vectors
+/** Dynamic shared memory of one CTA: control words + mbarrier, the 32x32 table, the two TMA-staged candidate windows, and the profile: per class K / 4 vectors
  *  of 32 strip slots x 16 bytes (the slot count is fixed so that vector offsets are compile-time constants). */
 inline size_t shared_bytes(int strip_index, int n_classes, bool compare) {
     size_t const profile = compare ? 0 : (size_t)n_classes * kStrips[strip_index] * 32 * 4;
-    return 16 + 1024 + profile;
+    return 16 + 1024 + 2 * kStageBytes + profile;
 }
 
 inline bool family_is_affine(int family) { return family == 1 || family == 3 || family == 5 || family == 7; }
