@@ -193,6 +193,24 @@ class DeviceGroup:
             self._lib.szs_b200_device_group_free(handle)
 
 
+def _prefer_bundled_nccl() -> None:
+    """The library resolves NCCL at run time (the copy already in the process, `SZS_B200_NCCL_LIBRARY`, or the system's
+    libnccl.so.2). A process that will also import torch must not pull in an OLDER system NCCL first — the two share a
+    soname and the first one loaded wins — so point the library at the copy torch bundles when there is one."""
+    import importlib.util
+    import os
+    from pathlib import Path
+
+    if "SZS_B200_NCCL_LIBRARY" in os.environ:
+        return
+    spec = importlib.util.find_spec("nvidia")
+    for root in (spec.submodule_search_locations if spec is not None else []):
+        candidate = Path(root) / "nccl" / "lib" / "libnccl.so.2"
+        if candidate.exists():
+            os.environ["SZS_B200_NCCL_LIBRARY"] = str(candidate)
+            return
+
+
 class Communicator:
     """One rank of a one-process-per-GPU job (`szs_b200_comm_*`): wraps an NCCL communicator created from C. Rank 0
     draws `Communicator.unique_id()` and passes the 128 bytes to the other ranks out of band (e.g. a
@@ -201,6 +219,7 @@ class Communicator:
     def __init__(self, unique_id: bytes, world_size: int, rank: int, gpu_device: int, library_path=None):
         if len(unique_id) != _abi.COMM_ID_BYTES:
             raise ValueError(f"unique_id must be {_abi.COMM_ID_BYTES} bytes")
+        _prefer_bundled_nccl()
         self._lib = _library(library_path)
         self._handle = ct.c_void_p()
         self.world_size, self.rank = int(world_size), int(rank)
@@ -211,6 +230,7 @@ class Communicator:
 
     @staticmethod
     def unique_id(library_path=None) -> bytes:
+        _prefer_bundled_nccl()
         buffer, message = ct.create_string_buffer(_abi.COMM_ID_BYTES), ct.c_char_p()
         _abi.check(_library(library_path).szs_b200_comm_unique_id(buffer, ct.byref(message)), message)
         return buffer.raw

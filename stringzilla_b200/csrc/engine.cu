@@ -1088,16 +1088,21 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
         by_length.swap(kept);
     }
     size_t const n_dp_candidates = by_length.size();
-    // A launch that cannot fill the GPU for ~50 us is folded into the next wider one: padding a few candidates to
-    // more words per lane costs less than a dependent launch of its own.
+    // Persistent warps drain a launch's tasks (one sweep of 32 / G queries each, all of similar duration) in rounds, and
+    // launches cannot share an SM, so every launch pays its own ramp and its own ragged last round. Unless the call is
+    // large enough for that to vanish (a dozen rounds per launch), all candidates join the widest launch: padding the
+    // shorter ones to more words per lane costs a few percent, a second half-empty round costs tens.
     if (myers_launches.size() > 1) {
         std::sort(myers_launches.begin(), myers_launches.end(),
                   [](MyersLaunch const &a, MyersLaunch const &b) { return a.words < b.words; });
+        uint64_t const pullers = myers_shared_table ? (uint64_t)device_sms : device_warps * 2;
+        auto tasks_of = [&](MyersLaunch const &launch) {
+            uint64_t tasks = 0;
+            for (MyersCandidate const &member : launch.members) tasks += (member.rows + 32 / member.lanes - 1) / (32 / member.lanes);
+            return myers_shared_table ? tasks / (kThreads / 32) : tasks;
+        };
         for (size_t l = 0; l + 1 < myers_launches.size();) {
-            uint64_t cells = 0;
-            for (MyersCandidate const &member : myers_launches[l].members)
-                cells += (uint64_t)candidate_length(member.candidate) * query_bytes_in_rows;
-            if (cells >= 1500000000ull) {
+            if (tasks_of(myers_launches[l]) >= 12 * pullers) {
                 ++l;
                 continue;
             }
