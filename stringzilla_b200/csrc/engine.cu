@@ -968,7 +968,8 @@ struct Schedule {
     std::vector<LaunchPlan> plans;  ///< DP tiers: one launch per (family, strip width)
     uint64_t scratch_words_per_cta = 0;
     std::vector<MyersLaunch> myers_launches; ///< bit-parallel tier, heaviest launch first
-    bool myers_shared_table = false;
+    bool myers_shared_table = false; ///< one match table per CTA (raw bytes or runes) instead of one per warp
+    bool myers_rune_table = false;   ///< ... whose rows are keyed by UTF-32 rune through a hash table
     int myers_rows = 0;
     uint64_t cells_total = 0, cells_u16 = 0, cells_myers = 0;
 };
@@ -1047,16 +1048,19 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     // one table per CTA whose rows are the bytes the candidate contains (bounded by the bytes any candidate contains).
     bool const myers_shared_table = schedule.myers_shared_table = model.scoring.compare != 0;
     int &myers_rows = schedule.myers_rows = model.scoring.n_classes;
-    if (myers_shared_table) {
+    bool const myers_rune_table = schedule.myers_rune_table = wide_symbols;
+    if (myers_rune_table) myers_rows = (int)std::min<uint32_t>(cs.longest, kRuneKernelLimit) + 1; // distinct runes <= length
+    else if (myers_shared_table) {
         myers_rows = 1;
         for (int b = 0; b < 256; ++b) myers_rows += present[b] != 0;
     }
-    if (unit_costs && engine.bit_parallel && !wide_symbols) {
+    if (unit_costs && engine.bit_parallel) {
         std::vector<uint32_t> kept;
         // Shared memory bounds the words per lane: a sixteenth of the SM per warp-private table (sixteen resident
         // warps per CTA), or the whole carve-out for a CTA-shared one.
         size_t const table_budget = myers_shared_table ? 220 * 1024 - 1024 : 12 * 1024;
-        int const max_words = (int)(table_budget / ((size_t)myers_rows * 32 * 4));
+        // Rune-keyed tables take one pattern word per lane: candidates of up to 1024 runes, longer ones stay on the DP tier.
+        int const max_words = myers_rune_table ? 1 : (int)(table_budget / ((size_t)myers_rows * 32 * 4));
         uint32_t remembered_length = 0xFFFFFFFFu;
         int remembered_words = 0, remembered_lanes = 0;
         MyersLaunch *remembered_launch = nullptr;
@@ -1088,21 +1092,18 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
         by_length.swap(kept);
     }
     size_t const n_dp_candidates = by_length.size();
-    // Persistent warps drain a launch's tasks (one sweep of 32 / G queries each, all of similar duration) in rounds, and
-    // launches cannot share an SM, so every launch pays its own ramp and its own ragged last round. Unless the call is
-    // large enough for that to vanish (a dozen rounds per launch), all candidates join the widest launch: padding the
-    // shorter ones to more words per lane costs a few percent, a second half-empty round costs tens.
+    // A launch that cannot fill the GPU for ~50 us is folded into the next wider one: padding a few candidates to
+    // more words per lane costs less than a dependent launch of its own. (Measured and rejected: folding EVERY launch of
+    // a small call into the widest one to save a ragged last round — c2 went from 37.8 to 35.8 TCUPS, i.e. exactly the
+    // extra words; the SMs are ALU-bound, so idle warps of a ragged round cost nothing, padding does.)
     if (myers_launches.size() > 1) {
         std::sort(myers_launches.begin(), myers_launches.end(),
                   [](MyersLaunch const &a, MyersLaunch const &b) { return a.words < b.words; });
-        uint64_t const pullers = myers_shared_table ? (uint64_t)device_sms : device_warps * 2;
-        auto tasks_of = [&](MyersLaunch const &launch) {
-            uint64_t tasks = 0;
-            for (MyersCandidate const &member : launch.members) tasks += (member.rows + 32 / member.lanes - 1) / (32 / member.lanes);
-            return myers_shared_table ? tasks / (kThreads / 32) : tasks;
-        };
         for (size_t l = 0; l + 1 < myers_launches.size();) {
-            if (tasks_of(myers_launches[l]) >= 12 * pullers) {
+            uint64_t cells = 0;
+            for (MyersCandidate const &member : myers_launches[l].members)
+                cells += (uint64_t)candidate_length(member.candidate) * query_bytes_in_rows;
+            if (cells >= 1500000000ull) {
                 ++l;
                 continue;
             }
@@ -1325,7 +1326,7 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
     std::vector<Job> const &host_jobs = schedule.jobs;
     std::vector<LaunchPlan> const &plans = schedule.plans;
     std::vector<MyersLaunch> const &myers_launches = schedule.myers_launches;
-    bool const myers_shared_table = schedule.myers_shared_table;
+    bool const myers_shared_table = schedule.myers_shared_table, myers_rune_table = schedule.myers_rune_table;
     int const myers_rows = schedule.myers_rows;
     uint64_t const scratch_words_per_cta = schedule.scratch_words_per_cta;
     uint64_t const cells_total = schedule.cells_total, cells_u16 = schedule.cells_u16, cells_myers = schedule.cells_myers;
@@ -1438,8 +1439,8 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
         for (size_t l = 0; l < myers_launches.size(); ++l) {
             MyersLaunch const &launch = myers_launches[l];
             int const warps = kThreads / 32;
-            size_t const smem = myers_shared_table
-                                    ? myers_shared_bytes(launch.words, myers_rows)
+            size_t const smem = myers_rune_table     ? myers_rune_bytes(myers_rows)
+                                : myers_shared_table ? myers_shared_bytes(launch.words, myers_rows)
                                     : (size_t)model.scoring.n_classes * 32 * launch.words * 4 * warps;
             int const ctas_per_sm = (!myers_shared_table && smem * 2 <= 220 * 1024) ? 2 : 1;
             // Work units that pull tasks: warps (private tables) or whole CTAs (shared table).
@@ -1471,7 +1472,8 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
             int const grid = myers_shared_table
                                  ? (int)std::min<uint64_t>(tasks, (uint64_t)device_sms)
                                  : (int)std::min<uint64_t>((tasks + warps - 1) / warps, (uint64_t)device_sms * ctas_per_sm);
-            SZB_CUDA(launch_myers(launch.words, myers_shared_table, grid, kThreads, smem, next_stream(), args));
+            int const table = myers_rune_table ? kMyersRuneTable : myers_shared_table ? kMyersSharedTable : kMyersPrivateTables;
+            SZB_CUDA(launch_myers(launch.words, table, grid, kThreads, smem, next_stream(), args));
             stats.kernel_launches++;
             first += launch.members.size();
         }

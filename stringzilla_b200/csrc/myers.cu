@@ -46,10 +46,24 @@ static cudaError_t launch_variant(int words, int grid, int threads, size_t smem,
     }
 }
 
-cudaError_t launch_myers(int words, bool shared_table, int grid, int threads, size_t smem, cudaStream_t stream,
-                         MyersArgs const &args) {
-    return shared_table ? launch_variant<true>(words, grid, threads, smem, stream, args)
-                        : launch_variant<false>(words, grid, threads, smem, stream, args);
+static cudaError_t launch_runes(int grid, int threads, size_t smem, cudaStream_t stream, MyersArgs const &args) {
+    static std::atomic<uint64_t> configured {0};
+    int device = 0;
+    cudaGetDevice(&device);
+    uint64_t const bit = device < 64 ? 1ull << device : 0;
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        cudaError_t status = cudaFuncSetAttribute(myers_rune_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (status != cudaSuccess) return status;
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    myers_rune_kernel<1><<<grid, threads, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_myers(int words, int table, int grid, int threads, size_t smem, cudaStream_t stream, MyersArgs const &args) {
+    if (table == kMyersRuneTable) return launch_runes(grid, threads, smem, stream, args);
+    return table == kMyersSharedTable ? launch_variant<true>(words, grid, threads, smem, stream, args)
+                                      : launch_variant<false>(words, grid, threads, smem, stream, args);
 }
 
 } // namespace szb
