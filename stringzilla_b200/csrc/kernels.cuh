@@ -306,8 +306,17 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         }
     }
 
+    // The affine packed families split every lane's strip into two sub-strips that run ONE ROW APART (sub-strip A on
+    // row r while sub-strip B finishes row r - 1): a lane then carries two independent dependency chains per step, which
+    // is what a CTA of four warps per scheduler needs to keep the DPX pipe fed (measured: the single-chain kernels stall
+    // on fixed-latency dependencies, ncu `stall_wait` 1.3 - 1.8 per issue). The wavefront becomes 2 G virtual lanes wide.
+    constexpr bool split = (FAM == FAM_AFF_SHIFT || FAM == FAM_SW_AFF) && K >= 16;
+    constexpr int VA = split ? (VECS + 1) / 2 : VECS; // vectors of sub-strip A
+    constexpr int KA = VA * 4;                        // columns of sub-strip A
+    constexpr int STRIDE = split ? 2 : 1;             // virtual lanes per lane
+
     // Number of steps: the longest query of the warp's groups plus the pipeline fill.
-    int steps = m > 0 ? m + G - 1 : 0;
+    int steps = m > 0 ? m + STRIDE * G - 1 : 0;
     for (int offset = 16; offset >= G; offset >>= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, offset));
 
     uint32_t a_next = (gl == 0 && m > 0) ? (wide ? q_wide[0] : (uint32_t)q_ptr[0]) : 0;
@@ -322,6 +331,94 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
     // Shared-window byte address of this lane's slot in profile row 0; a row is K / 4 vectors of 32 slots x 16 bytes.
     uint32_t const strip_address = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)gl * 16u;
     constexpr uint32_t row_bytes = (uint32_t)K * 32u * 4u;
+
+    // Sub-strip B's inputs: the row class and validity sub-strip A had one step ago, and the last cell of sub-strip A
+    // after the previous step (B's left neighbour) and after the one before (B's diagonal neighbour).
+    uint32_t a_b = 0, mid_w1 = split ? h[KA - 1] : 0, mid_w2 = mid_w1, mid_e1 = 0, e_b = 0;
+    bool valid_b = false;
+
+    auto add = [&](uint32_t x, uint32_t y) -> uint32_t {
+        if constexpr (packed) return add_on_fma_pipe(x, y, sc.one);
+        else return x + y;
+    };
+    // One DP cell: strip column k, diagonal sum t, left neighbour l, horizontal gap track e.
+    auto cell = [&](int k, uint32_t t, uint32_t &l, uint32_t &e, uint32_t a) {
+        if constexpr (traits::linear_shift) { l = h[k] = __vimax3_u16x2(t, h[k], l); }
+        else if constexpr (FAM == FAM_AFF_SHIFT) {
+            f[k] = __viaddmax_u16x2(h[k], sc.neg_go_bits, f[k]);
+            e = __viaddmax_u16x2(l, sc.neg_go_bits, e);
+            l = h[k] = __vimax3_u16x2(t, f[k], e);
+        }
+        else if constexpr (FAM == FAM_SW_LIN) {
+            uint32_t const up_gap = add(h[k], sc.gap_arith);
+            uint32_t const x = __vimax3_u16x2(t, up_gap, sc.bias_bits);
+            l = h[k] = __viaddmax_u16x2(l, sc.gap_bits, x);
+            if (k & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
+        }
+        else if constexpr (FAM == FAM_SW_AFF) {
+            // h[] holds H + open. The vertical track is floored at zero (exact: H is floored anyway and extend <= 0),
+            // which leaves ONE three-way maximum for the cell: 3 DPX + 3 FMA-pipe adds (+ half a DPX for the running max).
+            f[k] = __vimax3_u16x2(h[k], add(f[k], sc.ext_arith), sc.bias_bits);
+            e = __viaddmax_u16x2(e, sc.ext_bits, l);
+            l = h[k] = add(__vimax3_u16x2(t, e, f[k]), sc.open_arith);
+            if (k & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
+        }
+        else { // signed 32-bit cells, literal recurrences
+            int const ti = (int)t;
+            int score;
+            if constexpr (affine) {
+                int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
+                int const ins = __viaddmax_s32((int)l, open, (int)e + extend);
+                f[k] = (uint32_t)del, e = (uint32_t)ins;
+                score = __vimax3_s32(ti, del, ins);
+            }
+            else { score = __viaddmax_s32(max((int)h[k], (int)l), open, ti); }
+            if constexpr (local) {
+                score = max(score, 0);
+                // Gap rewards can inflate padding columns: only real cells compete.
+                if (cbase + k < (int)slot.len0) best = (uint32_t)max((int)best, score);
+            }
+            l = h[k] = (uint32_t)score;
+        }
+        (void)a;
+    };
+    // Compare modes form the substitution term of strip column k from the strip's symbols in registers.
+    auto compared = [&](int k, uint32_t a) -> uint32_t {
+        if constexpr (FAM == FAM_LIN_COMPARE) return sc.cmp_match_bits - __vminu2(cb[k] ^ (a * 0x01000100u), sc.cmp_drop_bits);
+        else if constexpr (!packed) return (uint32_t)(cb[k] == a ? sc.cmp_match : sc.cmp_mismatch);
+        else return 0u;
+    };
+    // Profile rows are stored ROTATED by one column: vector v of a strip holds the terms of its columns 4v+1 .. 4v+4, the
+    // last slot of the last vector the term of column 0. The diagonal sums of those columns are formed from the previous
+    // row's cells the moment the vector arrives — before any of them is overwritten — so every cell of the strip is
+    // updated in place and nothing has to be moved aside.
+    auto first_sum = [&](int k, uint32_t diagonal, uint32_t row_address, uint32_t a) -> uint32_t {
+        if (!compare) {
+            uint32_t term; // column k's term sits in the last slot of the vector before it (column 0: of the last vector)
+            uint32_t const slot_before = (uint32_t)((k == 0 ? VECS : k / 4) - 1) * 512u + 12u;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(term) : "r"(row_address + slot_before));
+            return add(diagonal, term);
+        }
+        return add(diagonal, compared(k, a));
+    };
+    auto vector = [&](int v, uint32_t row_address, uint32_t a, uint32_t &t_carry, uint32_t &l, uint32_t &e) {
+        uint32_t p[4];
+        if (!compare) {
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3])
+                         : "r"(row_address + (uint32_t)v * 512u));
+        }
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = compared((v * 4 + 1 + i) % K, a);
+        }
+        uint32_t t_next[4]; // diagonal sums of columns 4v+1 .. 4v+4 (the one past a sub-strip's end is not needed)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t_next[i] = add(h[v * 4 + i], p[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cell(v * 4 + i, i == 0 ? t_carry : t_next[i - 1], l, e, a);
+        t_carry = t_next[3];
+    };
 
     for (int s = 0; s < steps; ++s) {
         // Strip's left neighbour: the last cell of the lane to the left, one step ago.
@@ -339,10 +436,10 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
             else { w_in = bw_next, e_in = be_next; }
         }
 
-        bool const valid = valid_next; // this lane processes DP row r = s - gl + 1 in this step
+        bool const valid = valid_next; // (sub-strip A of) this lane processes DP row s - STRIDE * gl + 1 in this step
         uint32_t const a = a_next;
         {   // Prefetch the next row's class and (multi-pass) boundary cell.
-            int const next = s + 1 - gl;
+            int const next = s + 1 - STRIDE * gl;
             valid_next = (unsigned)next < (unsigned)m;
             if (valid_next) a_next = wide ? q_wide[next] : (uint32_t)q_ptr[next];
             if constexpr (MULTI) {
@@ -353,99 +450,62 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
             }
         }
 
-        if (valid) {
-            uint32_t l = w_in, e = e_in;
-            uint32_t const row_address = strip_address + a * row_bytes;
-            uint32_t const a_twice = a * 0x01000100u; // compare mode of the packed family: the row byte in both halves
-            // Compare modes form the substitution term of strip column k from the strip's symbols in registers.
-            auto compared = [&](int k) -> uint32_t {
-                if constexpr (FAM == FAM_LIN_COMPARE) return sc.cmp_match_bits - __vminu2(cb[k] ^ a_twice, sc.cmp_drop_bits);
-                else if constexpr (!packed) return (uint32_t)(cb[k] == a ? sc.cmp_match : sc.cmp_mismatch);
-                else return 0u;
-            };
-            auto add = [&](uint32_t x, uint32_t y) -> uint32_t {
-                if constexpr (packed) return add_on_fma_pipe(x, y, sc.one);
-                else return x + y;
-            };
-            // Profile rows are stored ROTATED by one column: vector v of a strip holds the terms of its columns
-            // 4v+1 .. 4v+4, the last slot of the last vector the term of column 0. The diagonal sums of those columns
-            // are formed from the previous row's cells the moment the vector arrives — before any of them is
-            // overwritten — so every cell of the strip is updated in place and nothing has to be moved aside.
-            uint32_t t_carry;
-            if (!compare) {
-                uint32_t first;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(first) : "r"(row_address + (uint32_t)(VECS - 1) * 512u + 12u));
-                t_carry = add(diag_in, first);
-            }
-            else { t_carry = add(diag_in, compared(0)); }
+        if constexpr (!split) {
+            if (valid) {
+                uint32_t l = w_in, e = e_in;
+                uint32_t const row_address = strip_address + a * row_bytes;
+                uint32_t t_carry = first_sum(0, diag_in, row_address, a);
 #pragma unroll
-            for (int v = 0; v < VECS; ++v) {
-                uint32_t p[4];
-                if (!compare) {
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3])
-                                 : "r"(row_address + (uint32_t)v * 512u));
-                }
-                else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) p[i] = compared((v * 4 + 1 + i) % K);
-                }
-                uint32_t t_next[4]; // diagonal sums of columns 4v+1 .. 4v+4 (the last one of the strip is not needed)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) t_next[i] = add(h[v * 4 + i], p[i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int const k = v * 4 + i;
-                    uint32_t const t = i == 0 ? t_carry : t_next[i - 1];
-                    if constexpr (traits::linear_shift) { l = h[k] = __vimax3_u16x2(t, h[k], l); }
-                    else if constexpr (FAM == FAM_AFF_SHIFT) {
-                        f[k] = __viaddmax_u16x2(h[k], sc.neg_go_bits, f[k]);
-                        e = __viaddmax_u16x2(l, sc.neg_go_bits, e);
-                        l = h[k] = __vimax3_u16x2(t, f[k], e);
+                for (int v = 0; v < VECS; ++v) vector(v, row_address, a, t_carry, l, e);
+                diag_in = w_in;
+                w_out = l, e_out = e;
+                if constexpr (MULTI) {
+                    if (to_scratch) {
+                        int const r = s - gl + 1; // the DP row just finished
+                        bnd[r * per_row] = l;
+                        if constexpr (affine) bnd[r * per_row + 1] = e;
                     }
-                    else if constexpr (FAM == FAM_SW_LIN) {
-                        uint32_t const up_gap = add(h[k], sc.gap_arith);
-                        uint32_t const x = __vimax3_u16x2(t, up_gap, sc.bias_bits);
-                        l = h[k] = __viaddmax_u16x2(l, sc.gap_bits, x);
-                        if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
-                    }
-                    else if constexpr (FAM == FAM_SW_AFF) {
-                        // h[] holds H + open. The vertical track is floored at zero (exact: H is floored anyway and
-                        // extend <= 0), which leaves ONE three-way maximum for the cell: 3 DPX + 3 FMA-pipe adds.
-                        f[k] = __vimax3_u16x2(h[k], add(f[k], sc.ext_arith), sc.bias_bits);
-                        e = __viaddmax_u16x2(e, sc.ext_bits, l);
-                        l = h[k] = add(__vimax3_u16x2(t, e, f[k]), sc.open_arith);
-                        if (i & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
-                    }
-                    else { // signed 32-bit cells, literal recurrences
-                        int const ti = (int)t;
-                        int score;
-                        if constexpr (affine) {
-                            int const del = __viaddmax_s32((int)h[k], open, (int)f[k] + extend);
-                            int const ins = __viaddmax_s32((int)l, open, (int)e + extend);
-                            f[k] = (uint32_t)del, e = (uint32_t)ins;
-                            score = __vimax3_s32(ti, del, ins);
-                        }
-                        else { score = __viaddmax_s32(max((int)h[k], (int)l), open, ti); }
-                        if constexpr (local) {
-                            score = max(score, 0);
-                            // Gap rewards can inflate padding columns: only real cells compete.
-                            if (cbase + k < (int)slot.len0) best = (uint32_t)max((int)best, score);
-                        }
-                        l = h[k] = (uint32_t)score;
-                    }
-                }
-                t_carry = t_next[3];
-            }
-            diag_in = w_in;
-            w_out = l, e_out = e;
-            if constexpr (MULTI) {
-                if (to_scratch) {
-                    int const r = s - gl + 1; // the DP row just finished
-                    bnd[r * per_row] = l;
-                    if constexpr (affine) bnd[r * per_row + 1] = e;
                 }
             }
+        }
+        else {
+            uint32_t const row_a = strip_address + a * row_bytes, row_b = strip_address + a_b * row_bytes;
+            uint32_t l_a = w_in, e_a = e_in, l_b = mid_w1;
+            e_b = mid_e1;
+            if (valid && valid_b) {
+                // Both sub-strips are live (all but the first and last step of a lane): one block, two chains.
+                uint32_t t_a = first_sum(0, diag_in, row_a, a), t_b = first_sum(KA, mid_w2, row_b, a_b);
+#pragma unroll
+                for (int v = 0; v < VA; ++v) {
+                    vector(v, row_a, a, t_a, l_a, e_a);
+                    if (VA + v < VECS) vector(VA + v, row_b, a_b, t_b, l_b, e_b);
+                }
+            }
+            else {
+                if (valid) {
+                    uint32_t t_a = first_sum(0, diag_in, row_a, a);
+#pragma unroll
+                    for (int v = 0; v < VA; ++v) vector(v, row_a, a, t_a, l_a, e_a);
+                }
+                if (valid_b) {
+                    uint32_t t_b = first_sum(KA, mid_w2, row_b, a_b);
+#pragma unroll
+                    for (int v = VA; v < VECS; ++v) vector(v, row_b, a_b, t_b, l_b, e_b);
+                }
+            }
+            if (valid_b) {
+                w_out = l_b, e_out = e_b;
+                if constexpr (MULTI) {
+                    if (to_scratch) {
+                        int const r = s - STRIDE * gl; // the DP row sub-strip B just finished
+                        bnd[r * per_row] = l_b;
+                        bnd[r * per_row + 1] = e_b;
+                    }
+                }
+            }
+            mid_w2 = mid_w1;
+            if (valid) diag_in = w_in, mid_w1 = l_a, mid_e1 = e_a;
+            valid_b = valid, a_b = a;
         }
     }
 
