@@ -418,7 +418,10 @@ class Bench:
             import torch.distributed as dist
 
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=self.device)
+            import datetime
+
+            # A short watchdog: a rank that fails must not leave its peers spinning in a collective for ten minutes.
+            dist.init_process_group("nccl", device_id=self.device, timeout=datetime.timedelta(seconds=180))
             self.dist = dist
             # torch.distributed is plumbing only: it carries the 128-byte NCCL identifier to the other ranks; the data
             # path of the e2e leg is the library's own communicator (one broadcast + one gather issued from C).
@@ -439,6 +442,12 @@ class Bench:
         if self.distributed:
             self.dist.all_reduce(tensor, op=self.dist.ReduceOp.MAX)
         return [float(v) for v in tensor]
+
+    def min_over_ranks(self, value):
+        tensor = self.torch.tensor([float(value)], dtype=self.torch.float64, device=self.device)
+        if self.distributed:
+            self.dist.all_reduce(tensor, op=self.dist.ReduceOp.MIN)
+        return float(tensor[0])
 
     def partition(self, lengths, symmetric=False):
         bounds = np.zeros(self.world + 1, dtype=np.uint64)
@@ -479,6 +488,7 @@ class Bench:
             first_call = time.perf_counter() - first_call
             if budget_seconds:
                 reps = max(2, min(reps, int(budget_seconds / max(first_call, 1e-4))))
+                reps = int(self.min_over_ranks(reps))  # every rank must enter the same number of collective steps
             for _ in range(max(0, warmup - 1)):
                 resident_step(current)
             events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]

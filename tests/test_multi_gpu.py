@@ -165,5 +165,16 @@ def test_two_ranks_exchange_over_nccl():
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under `gpurun --gpus 2`)")
+    import time
+
     with tempfile.TemporaryDirectory() as directory:
-        mp.spawn(_two_rank_worker, args=(os.path.join(directory, "nccl_id"), 5), nprocs=2, join=True)
+        # A rank that fails leaves its peer blocked inside a collective: never wait for the children without a deadline.
+        context = mp.spawn(_two_rank_worker, args=(os.path.join(directory, "nccl_id"), 5), nprocs=2, join=False)
+        deadline = time.monotonic() + 420
+        try:
+            while not context.join(timeout=5):
+                assert time.monotonic() < deadline, "the two-rank exchange did not finish in time"
+        finally:
+            for process in context.processes:
+                if process.is_alive():
+                    process.kill()

@@ -267,15 +267,26 @@ def test_utf8_levenshtein_rune_level(scope):
         assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, candidates, *costs)), costs
     got = szb.LevenshteinDistancesUTF8()(queries, device=scope)
     assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, None))
-    # More than 256 distinct runes in one call: no byte ranking exists, the 32-bit symbol recurrences take over.
+    # More than 256 distinct runes in one call: no byte ranking exists. Unit costs take the rune-keyed bit-parallel kernel
+    # (candidates of up to 1024 runes; the 1500-rune one stays on the 32-bit symbol recurrences), other costs the
+    # 32-bit symbol recurrences.
     cjk = [chr(0x4E00 + i) for i in range(2000)]
     wide_text = lambda n: "".join(cjk[i] for i in rng.integers(0, len(cjk), size=n)).encode()
-    wide_q = [wide_text(int(n)) for n in rng.integers(0, 500, size=7)] + [text(40)]
-    wide_c = [wide_text(int(n)) for n in rng.integers(0, 700, size=6)] + [wide_q[0][: 3 * 50], b"ascii too"]
+    wide_q = [wide_text(int(n)) for n in rng.integers(0, 500, size=7)] + [text(40), wide_text(1024), wide_text(1100)]
+    wide_c = [wide_text(int(n)) for n in rng.integers(0, 700, size=6)] + [wide_q[0][: 3 * 50], b"ascii too", wide_text(1),
+                                                                          wide_text(33), wide_text(1024), wide_text(1500)]
     for costs in ((0, 1, 1, 1), (0, 4, 3, 2)):
         engine = szb.LevenshteinDistancesUTF8(*costs)
         assert np.array_equal(engine(wide_q, wide_c, device=scope), support.oracle_levenshtein_utf8(wide_q, wide_c, *costs))
-        assert engine.last_call_stats.pairs_s32 > 0
+        stats = engine.last_call_stats
+        assert stats.pairs_s32 > 0 and (stats.pairs_bit_parallel > 0) == (costs == (0, 1, 1, 1))
+    # The rune-keyed kernel over every wavefront width (1 .. 32 lanes of one 32-bit word), symmetric call included.
+    many_c = [wide_text(n) for n in (1, 31, 32, 33, 64, 65, 128, 129, 256, 257, 512, 513, 1000, 1024)]
+    many_q = [wide_text(int(n)) for n in rng.integers(0, 1200, size=40)]
+    rune_engine = szb.LevenshteinDistancesUTF8()
+    assert np.array_equal(rune_engine(many_q, many_c, device=scope), support.oracle_levenshtein_utf8(many_q, many_c))
+    assert rune_engine.last_call_stats.pairs_s32 == 0
+    assert np.array_equal(rune_engine(many_c, device=scope), support.oracle_levenshtein_utf8(many_c, None))
     few = szb.LevenshteinDistancesUTF8()
     assert np.array_equal(few(queries, candidates, device=scope), support.oracle_levenshtein_utf8(queries, candidates))
     assert few.last_call_stats.pairs_bit_parallel > 0  # ~40 distinct runes: ranked into bytes, bit-parallel kernel

@@ -126,7 +126,7 @@ def test_reference_benchmark_runs_the_b200_engines(tmp_path):
     env = dict(os.environ, STRINGWARS_DATASET=str(dataset), STRINGWARS_TOKENS="lines", STRINGWARS_DURATION="1",
                STRINGWARS_STRESS="1", STRINGWARS_STRESS_DURATION="1", STRINGWARS_STRESS_DIR=str(tmp_path),
                STRINGWARS_FILTER="_b200", STRINGWARS_BATCH="24")
-    done = subprocess.run([str(binary)], env=env, capture_output=True, text=True, timeout=900)
+    done = subprocess.run([str(binary)], env=env, capture_output=True, text=True, timeout=420)
     out = done.stdout + done.stderr
     assert done.returncode == 0, out[-3000:]
     assert "All benchmarks finished." in out and "Mismatch" not in out and "> Errors" not in out, out[-3000:]
