@@ -47,6 +47,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+/** Two sub-strips per lane in the affine packed kernels (see `sweep_batch`): measured slower, kept as an experiment. */
+#ifndef SZB_SPLIT_STRIPS
+#define SZB_SPLIT_STRIPS 0
+#endif
+
 namespace szb {
 
 enum Family : int {
@@ -306,11 +311,14 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         }
     }
 
-    // The affine packed families split every lane's strip into two sub-strips that run ONE ROW APART (sub-strip A on
-    // row r while sub-strip B finishes row r - 1): a lane then carries two independent dependency chains per step, which
-    // is what a CTA of four warps per scheduler needs to keep the DPX pipe fed (measured: the single-chain kernels stall
-    // on fixed-latency dependencies, ncu `stall_wait` 1.3 - 1.8 per issue). The wavefront becomes 2 G virtual lanes wide.
-    constexpr bool split = (FAM == FAM_AFF_SHIFT || FAM == FAM_SW_AFF) && K >= 16;
+    // EXPERIMENT, off by default (-DSZB_SPLIT_STRIPS=1): the affine packed families split every lane's strip into two
+    // sub-strips that run ONE ROW APART (sub-strip A on row r while sub-strip B finishes row r - 1), so that a lane carries
+    // two independent dependency chains per step and the wavefront becomes 2 G virtual lanes wide. Measured on c3 / c3_sw /
+    // c4: 6.9 / 5.2 / 5.0 TCUPS against 7.9 / 6.2 / 5.7 without it. The SASS-level profile of the single-chain kernel
+    // explains why: with four warps per scheduler every dependent DPX instruction already costs a warp ~8 cycles
+    // (wait + pipe throttle + not selected), i.e. the four warps together issue one DPX instruction every 2 cycles, which
+    // IS the pipe's rate; the chain phase is not where the idle pipe cycles are.
+    constexpr bool split = SZB_SPLIT_STRIPS != 0 && (FAM == FAM_AFF_SHIFT || FAM == FAM_SW_AFF) && K >= 16;
     constexpr int VA = split ? (VECS + 1) / 2 : VECS; // vectors of sub-strip A
     constexpr int KA = VA * 4;                        // columns of sub-strip A
     constexpr int STRIDE = split ? 2 : 1;             // virtual lanes per lane

@@ -130,7 +130,7 @@ def test_reference_benchmark_runs_the_b200_engines(tmp_path):
     out = done.stdout + done.stderr
     assert done.returncode == 0, out[-3000:]
     assert "All benchmarks finished." in out and "Mismatch" not in out and "> Errors" not in out, out[-3000:]
-    names = re.findall(r"Benchmarking `([^`]+)`", out)
+    names = re.findall(r"Benchmarking (?:\x1b\[1m)?`([^`]+)`", out)  # the reference prints the name in bold
     for expected in ("levenshtein_b200_unit", "affine_levenshtein_b200_weird", "needleman_wunsch_b200", "smith_waterman_b200",
                      "affine_needleman_wunsch_b200", "affine_smith_waterman_b200"):
         assert any(name.startswith(expected + ":") for name in names), (expected, names)
