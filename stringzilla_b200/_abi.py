@@ -121,6 +121,8 @@ COMM_ID_BYTES = 128
 
 def bind(path: os.PathLike | str | None = None) -> ct.CDLL:
     """Loads a library exporting the `szs_*` ABI and attaches prototypes. No fallback: a missing file raises."""
+    if path is None and os.environ.get("SZS_B200_LIBRARY"):  # kernel experiments: a variant build of the same library
+        path = os.environ["SZS_B200_LIBRARY"]
     path = Path(path) if path is not None else DEFAULT_LIBRARY
     if not path.exists():
         raise FileNotFoundError(

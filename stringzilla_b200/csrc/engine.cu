@@ -385,6 +385,7 @@ struct StagedSet {
     uint8_t const *blob = nullptr;           // tapes: first byte of the collection
     sz_sequence_t const *sequence = nullptr; // callback sequences
     bool host_readable = true;               // the bytes can be read by host code (pageable, pinned or managed memory)
+    bool host_resident = true;               // ... and live in host memory proper (managed pages may sit on the device)
     uint8_t const *host_view = nullptr;      // the bytes as one host-readable run, when there is one
     bool uploaded = false;                   // the raw bytes are in `raw`
     DeviceBuffer raw, classes, device_offsets;
@@ -477,7 +478,7 @@ static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) 
     set.count = count;
     set.offsets.resize(count + 1);
     set.longest = 0, set.blob = nullptr, set.sequence = nullptr, set.host_view = nullptr, set.uploaded = false;
-    set.host_readable = true;
+    set.host_readable = true, set.host_resident = true;
 
     if (view.layout == InputView::kTape32 || view.layout == InputView::kTape64) {
         void const *offsets_pointer;
@@ -523,7 +524,9 @@ static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) 
             blob += first;
         }
         set.blob = blob;
-        set.host_readable = set.total_bytes == 0 || pointer_is_host_readable(blob);
+        MemoryKind const kind = set.total_bytes == 0 ? MemoryKind::kPageable : memory_kind(blob);
+        set.host_readable = kind != MemoryKind::kDevice;
+        set.host_resident = kind == MemoryKind::kPageable || kind == MemoryKind::kPinned;
         if (set.host_readable) set.host_view = blob;
     }
     else {
@@ -540,7 +543,10 @@ static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) 
         set.offsets[count] = (uint32_t)running;
         set.total_bytes = running;
         // Like the reference (cuda.cuh:4268-4272), only the first string's pointer is inspected.
-        set.host_readable = count == 0 || running == 0 || pointer_is_host_readable(sequence->get_start(sequence->handle, 0));
+        MemoryKind const kind =
+            (count == 0 || running == 0) ? MemoryKind::kPageable : memory_kind(sequence->get_start(sequence->handle, 0));
+        set.host_readable = kind != MemoryKind::kDevice;
+        set.host_resident = kind == MemoryKind::kPageable || kind == MemoryKind::kPinned;
     }
     return ok();
 }
@@ -771,7 +777,7 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
         // Small host-resident inputs are scanned on the host: a kernel plus a D2H round-trip costs more than the scan.
         constexpr uint64_t host_scan_limit = 512 * 1024;
         auto scannable = [&](StagedSet const &set) {
-            return !set.total_bytes || (set.total_bytes <= host_scan_limit && set.host_readable && (set.host_view || packed));
+            return !set.total_bytes || (set.total_bytes <= host_scan_limit && set.host_resident && (set.host_view || packed));
         };
         if (scannable(cs) && (!need_queries || scannable(qs))) {
             auto scan = [](StagedSet const &set, uint32_t (&seen)[256]) {
@@ -1279,7 +1285,8 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
         return fail(sz_overflow_risk_k, "Too many strings for one call");
 
     // Small host-resident inputs never get a copy of their own: the host maps them to classes straight into the arena.
-    bool packed = caller_queries.host_readable && caller_candidates.host_readable &&
+    // (Managed memory is left to the copy engine: touching it from the host would pull its pages back from the device.)
+    bool packed = caller_queries.host_resident && caller_candidates.host_resident &&
                   caller_queries.total_bytes + (symmetric ? 0 : caller_candidates.total_bytes) <= kPackedLimit;
     if (!packed) {
         if (Failure failure = upload_raw(caller_queries, stream, stats)) return failure;

@@ -47,6 +47,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+/** Smith-Waterman affine, variant: cells stored as H (not H + open), the `+ open` of both gap tracks formed by adds off
+ *  the dependency chain (4 FMA-pipe adds per cell pair instead of 3, a 2-op instead of a 3-op chain per cell). */
+#ifndef SZB_SW_SHORT_CHAIN
+#define SZB_SW_SHORT_CHAIN 0
+#endif
+
 /** Two sub-strips per lane in the affine packed kernels (see `sweep_batch`): measured slower, kept as an experiment. */
 #ifndef SZB_SPLIT_STRIPS
 #define SZB_SPLIT_STRIPS 0
@@ -135,7 +141,9 @@ __device__ __forceinline__ int profile_term(int8_t const *sub, int a, int b, boo
     if constexpr (family_traits<FAM>::linear_shift) { return valid ? max(s - 2 * open, 0) : 0; }
     else if constexpr (FAM == FAM_AFF_SHIFT) { return valid ? max(s, 2 * open) - 2 * extend : 2 * (open - extend); }
     else if constexpr (FAM == FAM_SW_LIN) { return valid ? s : -bias; }
-    else if constexpr (FAM == FAM_SW_AFF) { return valid ? s - open : -open - bias; } // cells are kept as H + open
+    else if constexpr (FAM == FAM_SW_AFF) { // cells are kept as H + open (unless SZB_SW_SHORT_CHAIN)
+        return SZB_SW_SHORT_CHAIN ? (valid ? s : -bias) : (valid ? s - open : -open - bias);
+    }
     else { return valid ? s : -(1 << 28); }
 }
 
@@ -283,7 +291,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
     }
     else if constexpr (FAM == FAM_SW_AFF) {
         // Cells are kept as H + open (what both gap tracks consume); the vertical track is kept floored at zero.
-        uint32_t const zero_cell = pack_bits(bias + open);
+        uint32_t const zero_cell = pack_bits(bias + (SZB_SW_SHORT_CHAIN ? 0 : open));
 #pragma unroll
         for (int k = 0; k < K; ++k) h[k] = zero_cell, f[k] = sc.bias_bits;
         diag_in = zero_cell;
@@ -366,9 +374,16 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         else if constexpr (FAM == FAM_SW_AFF) {
             // h[] holds H + open. The vertical track is floored at zero (exact: H is floored anyway and extend <= 0),
             // which leaves ONE three-way maximum for the cell: 3 DPX + 3 FMA-pipe adds (+ half a DPX for the running max).
-            f[k] = __vimax3_u16x2(h[k], add(f[k], sc.ext_arith), sc.bias_bits);
-            e = __viaddmax_u16x2(e, sc.ext_bits, l);
-            l = h[k] = add(__vimax3_u16x2(t, e, f[k]), sc.open_arith);
+            if constexpr (SZB_SW_SHORT_CHAIN != 0) {
+                f[k] = __vimax3_u16x2(add(h[k], sc.open_arith), add(f[k], sc.ext_arith), sc.bias_bits);
+                e = __viaddmax_u16x2(l, sc.gap_bits, add(e, sc.ext_arith));
+                l = h[k] = __vimax3_u16x2(t, e, f[k]);
+            }
+            else {
+                f[k] = __vimax3_u16x2(h[k], add(f[k], sc.ext_arith), sc.bias_bits);
+                e = __viaddmax_u16x2(e, sc.ext_bits, l);
+                l = h[k] = add(__vimax3_u16x2(t, e, f[k]), sc.open_arith);
+            }
             if (k & 1) best = __vimax3_u16x2(best, h[k - 1], h[k]);
         }
         else { // signed 32-bit cells, literal recurrences
@@ -557,7 +572,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
                 if constexpr (packed) group_best = __vmaxu2(group_best, other);
                 else group_best = (uint32_t)max((int)group_best, (int)other);
             }
-            int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias - (FAM == FAM_SW_AFF ? open : 0)
+            int64_t score = packed ? (int64_t)((group_best >> (16 * half)) & 0xFFFFu) - bias - ((FAM == FAM_SW_AFF && !SZB_SW_SHORT_CHAIN) ? open : 0)
                                    : (int64_t)(int)group_best;
             if (gl == 0 && q_valid) {
                 // Later passes of a long candidate fold into the cell written by pass 0 (same CTA, ordered by
