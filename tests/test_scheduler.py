@@ -103,3 +103,37 @@ def test_extreme_shapes():
     check_invariants(*plan(szb.LevenshteinDistances(1, 3, 3, 3), [5], np.full(100000, 3)))
     check_invariants(*plan(szb.LevenshteinDistances(1, 3, 3, 3), np.full(50000, 7), [9]))
     check_invariants(*plan(szb.LevenshteinDistances(2, 3, 4, 1), [70000, 3], [65000, 123456, 0]))
+
+
+def test_calls_too_small_to_fill_the_device_take_latency_shapes():
+    """A call with fewer pairs than the device has warps is bound by the latency of one sweep: each pair is spread over
+    as many lanes as there are idle ones (one word per lane for a single 1024-character pair, the widest DP wavefront)."""
+    unit = szb.LevenshteinDistances()
+    q, c, assignment, partner, order, jobs = plan(unit, [1024], [1024])
+    tier, width, lanes = assignment & 0xFF, (assignment >> 8) & 0xFF, (assignment >> 16) & 0xFF
+    assert tier[0] == TIER_BIT_PARALLEL and lanes[0] == 32 and width[0] == 1
+    # c1: 32 x 32 pairs of 64..256 characters still leave most warps idle: at least 8 lanes per pair.
+    rng = np.random.default_rng(5)
+    q, c, assignment, partner, order, jobs = plan(unit, rng.integers(64, 257, size=32), rng.integers(64, 257, size=32))
+    assert ((assignment & 0xFF) == TIER_BIT_PARALLEL).all() and (((assignment >> 16) & 0xFF) >= 8).all()
+    check_invariants(q, c, assignment, partner, order, jobs)
+    # The c2 tile fills the device: the tightest coverage wins again (4 lanes of 8 or 9 words).
+    q, c, assignment, partner, order, jobs = plan(unit, rng.integers(960, 1089, size=316), rng.integers(960, 1089, size=317))
+    assert set(((assignment >> 16) & 0xFF).tolist()) == {4} and set(((assignment >> 8) & 0xFF).tolist()) <= {8, 9}
+    # DP tier of a tiny call: the widest wavefront (32 lanes).
+    weird = szb.LevenshteinDistances(1, 3, 3, 3)
+    q, c, assignment, partner, order, jobs = plan(weird, [700, 650], [600, 640, 100])
+    assert ((assignment & 0xFF) == TIER_PACKED).all() and (((assignment >> 16) & 0xFF) == 32).all()
+    check_invariants(q, c, assignment, partner, order, jobs)
+
+
+def test_jobs_are_single_rounds_on_large_tiles():
+    """Jobs are cut to ~24 per SM so that the ragged end of a persistent launch costs a few percent: on the c3 tile every
+    job is one round of the CTA's sixteen warps."""
+    byte_to_class, table = scoring.blosum62()
+    engine = szb.NeedlemanWunschScores(byte_to_class, table, open=-4, extend=-1)
+    rng = np.random.default_rng(6)
+    q, c, assignment, partner, order, jobs = plan(engine, rng.integers(960, 1089, size=316), rng.integers(960, 1089, size=317),
+                                                  distinct_bytes=20)
+    check_invariants(q, c, assignment, partner, order, jobs)
+    assert len(jobs) >= 148 * 16 and max(end - begin for _, begin, end in jobs.tolist()) == 16
