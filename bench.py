@@ -770,7 +770,7 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # The same tile our arm scores at this GPU count: weak scaling grows the query rows with the number of ranks.
     label, family, kwargs, queries, candidates = make_workload(args.workload, scale=world if args.scaling == "weak" else 1)
-    reference = time_reference(family, kwargs, queries, candidates, steps=args.steps, warmup=args.warmup, budget_seconds=120)
+    reference = time_reference(family, kwargs, queries, candidates, steps=args.steps, warmup=args.warmup, budget_seconds=80)
     if reference is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libstringzillas_ref.so is not built"}))
         return
