@@ -386,6 +386,7 @@ struct StagedSet {
     sz_sequence_t const *sequence = nullptr; // callback sequences
     bool host_readable = true;               // the bytes can be read by host code (pageable, pinned or managed memory)
     bool host_resident = true;               // ... and live in host memory proper (managed pages may sit on the device)
+    bool pageable = false;                   // ... unregistered host memory: DMA needs a pinned bounce buffer
     uint8_t const *host_view = nullptr;      // the bytes as one host-readable run, when there is one
     bool uploaded = false;                   // the raw bytes are in `raw`
     DeviceBuffer raw, classes, device_offsets;
@@ -478,7 +479,7 @@ static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) 
     set.count = count;
     set.offsets.resize(count + 1);
     set.longest = 0, set.blob = nullptr, set.sequence = nullptr, set.host_view = nullptr, set.uploaded = false;
-    set.host_readable = true, set.host_resident = true;
+    set.host_readable = true, set.host_resident = true, set.pageable = false;
 
     if (view.layout == InputView::kTape32 || view.layout == InputView::kTape64) {
         void const *offsets_pointer;
@@ -527,6 +528,7 @@ static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) 
         MemoryKind const kind = set.total_bytes == 0 ? MemoryKind::kPageable : memory_kind(blob);
         set.host_readable = kind != MemoryKind::kDevice;
         set.host_resident = kind == MemoryKind::kPageable || kind == MemoryKind::kPinned;
+        set.pageable = kind == MemoryKind::kPageable;
         if (set.host_readable) set.host_view = blob;
     }
     else {
@@ -551,6 +553,9 @@ static Failure read_layout(InputView view, StagedSet &set, cudaStream_t stream) 
     return ok();
 }
 
+/** Pageable blobs of at least this many bytes are staged through pinned memory by several host threads. */
+constexpr uint64_t kParallelStagingBytes = 4ull << 20;
+
 /** Copies the raw bytes of one collection to the device (`set.raw`). Accepts host, pinned, managed or device memory. */
 static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_stats_t &stats) {
     // Padding keeps the 16-byte vector loads of the class-mapping kernel in bounds.
@@ -559,6 +564,47 @@ static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_sta
     set.uploaded = true;
     if (!set.total_bytes) return ok();
     if (!set.sequence) {
+        if (set.pageable && set.total_bytes >= kParallelStagingBytes) {
+            // A large blob in pageable memory (a retrieval corpus): the driver would bounce it through its own pinned
+            // buffer with one host thread. A few host threads copy it into the engine's pinned buffer chunk by chunk while
+            // the copy engine drains the finished chunks.
+            SZB_CUDA(set.gather.reserve(set.total_bytes));
+            uint64_t const chunk = 1ull << 20, n_chunks = (set.total_bytes + chunk - 1) / chunk;
+            std::vector<std::atomic<uint8_t>> done(n_chunks);
+            for (auto &flag : done) flag.store(0, std::memory_order_relaxed);
+            std::atomic<uint64_t> next {0};
+            unsigned const n_threads = (unsigned)std::min<uint64_t>(std::max(2u, std::min(6u, std::thread::hardware_concurrency() / 2)), n_chunks);
+            auto worker = [&] {
+                for (uint64_t i = next.fetch_add(1); i < n_chunks; i = next.fetch_add(1)) {
+                    uint64_t const begin = i * chunk, bytes = std::min(chunk, set.total_bytes - begin);
+                    std::memcpy((char *)set.gather.ptr + begin, set.blob + begin, bytes);
+                    done[i].store(1, std::memory_order_release);
+                }
+            };
+            std::vector<std::thread> threads;
+            for (unsigned t = 0; t + 1 < n_threads; ++t) threads.emplace_back(worker);
+            cudaError_t error = cudaSuccess;
+            for (uint64_t i = 0; i < n_chunks; ++i) {
+                while (!done[i].load(std::memory_order_acquire)) {
+                    // Help with the copying instead of spinning.
+                    uint64_t const mine = next.fetch_add(1);
+                    if (mine < n_chunks) {
+                        uint64_t const begin = mine * chunk, bytes = std::min(chunk, set.total_bytes - begin);
+                        std::memcpy((char *)set.gather.ptr + begin, set.blob + begin, bytes);
+                        done[mine].store(1, std::memory_order_release);
+                    }
+                    else std::this_thread::yield();
+                }
+                uint64_t const begin = i * chunk, bytes = std::min(chunk, set.total_bytes - begin);
+                if (error == cudaSuccess)
+                    error = cudaMemcpyAsync((char *)set.raw.ptr + begin, (char *)set.gather.ptr + begin, bytes, cudaMemcpyHostToDevice, stream);
+            }
+            for (std::thread &thread : threads) thread.join();
+            SZB_CUDA(error);
+            stats.h2d_bytes += set.total_bytes;
+            set.host_view = (uint8_t const *)set.gather.ptr;
+            return ok();
+        }
         SZB_CUDA(cudaMemcpyAsync(set.raw.ptr, set.blob, set.total_bytes, cudaMemcpyDefault, stream));
         if (set.host_readable) stats.h2d_bytes += set.total_bytes;
         return ok();

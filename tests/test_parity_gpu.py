@@ -554,3 +554,21 @@ def test_full_size_tile_properties_and_sampled_parity(scope):
     assert np.array_equal(transposed, matrix.T)
     stats = engine.last_call_stats
     assert stats.cells == int(lengths_q.sum()) * int(lengths_c.sum()) and stats.kernel_launches >= 1
+
+
+def test_large_pageable_corpus_is_staged_in_parallel(scope):
+    """A candidate blob of more than 4 MB in pageable memory takes the multi-threaded pinned staging path (a retrieval
+    corpus against a couple of queries, which also trades roles); results must not depend on how the bytes travelled."""
+    rng = np.random.default_rng(67)
+    corpus = support.random_strings(rng, 4600, 900, 1000, support.DNA)
+    queries = support.random_strings(rng, 2, 400, 600, support.DNA)
+    tape = szb.Tape(corpus)
+    assert tape.data.nbytes > 4 << 20
+    engine = szb.LevenshteinDistances()
+    got = engine(queries, tape, device=scope)
+    assert np.array_equal(got, support.oracle_levenshtein(queries, tape))
+    assert engine.last_call_stats.h2d_bytes >= tape.data.nbytes
+    # The same corpus as the query side of a weighted engine (no role swap: 3 candidates, 4600 rows).
+    weird = szb.LevenshteinDistances(1, 3, 3, 3)
+    few = support.random_strings(rng, 3, 100, 200, support.DNA)
+    assert np.array_equal(weird(tape, few, device=scope), support.oracle_levenshtein(tape, few, 1, 3, 3, 3))
