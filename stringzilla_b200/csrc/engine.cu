@@ -61,6 +61,16 @@ __global__ void map_classes_kernel(uint8_t const *in, uint8_t *out, uint64_t n, 
     }
 }
 
+/** Callback sequences whose strings live in managed or device memory: one warp per string copies it into the blob. */
+__global__ void gather_strings_kernel(uint8_t const *const *starts, uint32_t const *offsets, uint32_t count, uint8_t *out) {
+    uint32_t const lane = threadIdx.x & 31, warps = gridDim.x * (blockDim.x / 32);
+    for (uint32_t i = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; i < count; i += warps) {
+        uint32_t const begin = offsets[i], length = offsets[i + 1] - begin;
+        uint8_t const *const source = starts[i];
+        for (uint32_t b = lane; b < length; b += 32) out[begin + b] = source[b];
+    }
+}
+
 /** Marks which byte values occur in a blob: flags[b] != 0. Drives the Levenshtein alphabet compaction. */
 __global__ void byte_presence_kernel(uint8_t const *in, uint64_t n, uint32_t *flags) {
     __shared__ uint32_t seen[256];
@@ -389,13 +399,13 @@ struct StagedSet {
     bool pageable = false;                   // ... unregistered host memory: DMA needs a pinned bounce buffer
     uint8_t const *host_view = nullptr;      // the bytes as one host-readable run, when there is one
     bool uploaded = false;                   // the raw bytes are in `raw`
-    DeviceBuffer raw, classes, device_offsets;
+    DeviceBuffer raw, classes, device_offsets, gather_list;
     DeviceBuffer rune_counts, rune_offsets, runes; // UTF-8 engines: the decoded symbol streams
     std::vector<uint32_t> rune_counts_host;
     PinnedBuffer gather; // only for callback sequences
     std::vector<uint8_t> offsets_bounce;
     void release() {
-        raw.release(), classes.release(), device_offsets.release(), rune_counts.release(), rune_offsets.release();
+        raw.release(), classes.release(), device_offsets.release(), gather_list.release(), rune_counts.release(), rune_offsets.release();
         runes.release(), gather.release();
     }
     /** Calls `visit(pointer, length, index)` for every string; only valid when `host_readable`. */
@@ -610,7 +620,7 @@ static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_sta
         return ok();
     }
     sz_sequence_t const *sequence = set.sequence;
-    if (set.host_readable) {
+    if (set.host_resident) {
         SZB_CUDA(set.gather.reserve(set.total_bytes));
         set.for_each_host_string([&](uint8_t const *start, size_t length, size_t i) {
             if (length) std::memcpy((char *)set.gather.ptr + set.offsets[i], start, length);
@@ -620,12 +630,22 @@ static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_sta
         set.host_view = (uint8_t const *)set.gather.ptr;
         return ok();
     }
-    for (size_t i = 0; i < set.count; ++i) {
-        size_t const length = set.offsets[i + 1] - set.offsets[i];
-        if (length)
-            SZB_CUDA(cudaMemcpyAsync((char *)set.raw.ptr + set.offsets[i], sequence->get_start(sequence->handle, i),
-                                     length, cudaMemcpyDefault, stream));
-    }
+    // Managed or device memory: the strings are gathered ON the device from an uploaded pointer list (the host never
+    // touches managed pages that may sit on the device, and device strings need no per-string copy calls).
+    size_t const pointer_bytes = set.count * sizeof(void *), offset_bytes = (set.count + 1) * sizeof(uint32_t);
+    SZB_CUDA(set.gather.reserve(pointer_bytes + offset_bytes));
+    SZB_CUDA(set.gather_list.reserve(pointer_bytes + offset_bytes));
+    void const **const pointers = (void const **)set.gather.ptr;
+    for (size_t i = 0; i < set.count; ++i) pointers[i] = sequence->get_start(sequence->handle, i);
+    std::memcpy((char *)set.gather.ptr + pointer_bytes, set.offsets.data(), offset_bytes);
+    SZB_CUDA(cudaMemcpyAsync(set.gather_list.ptr, set.gather.ptr, pointer_bytes + offset_bytes, cudaMemcpyHostToDevice, stream));
+    stats.h2d_bytes += pointer_bytes + offset_bytes;
+    int const blocks = (int)std::min<size_t>((set.count + 7) / 8, 4096);
+    gather_strings_kernel<<<blocks, 256, 0, stream>>>((uint8_t const *const *)set.gather_list.ptr,
+                                                      (uint32_t const *)((char *)set.gather_list.ptr + pointer_bytes),
+                                                      (uint32_t)set.count, set.raw.as<uint8_t>());
+    SZB_CUDA(cudaGetLastError());
+    stats.kernel_launches++;
     return ok();
 }
 

@@ -333,6 +333,30 @@ def test_every_input_layout_of_the_abi(scope):
                                            5, ct.byref(message))
     assert status == 0 and np.array_equal(got, want)
 
+    # Callback sequences whose strings live in managed memory (the reference bench's `unified_alloc` tokens) and in device
+    # memory: the strings are gathered on the device from an uploaded pointer list, the host never reads them.
+    import torch
+
+    def sequence_in(strings, base_address):
+        offsets = np.concatenate([[0], np.cumsum([len(s) for s in strings])]).astype(np.int64)
+        start = _abi.SEQUENCE_START(lambda _, i: base_address + int(offsets[i]))
+        length = _abi.SEQUENCE_LENGTH(lambda _, i: len(strings[i]))
+        return _abi.Sequence(None, len(strings), start, length), (start, length, offsets)
+
+    blob = b"".join(queries) + b"".join(candidates)
+    split = sum(len(s) for s in queries)
+    managed = lib.szs_unified_alloc(len(blob))
+    ct.memmove(managed, blob, len(blob))
+    device_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+    for base in (managed, device_blob.data_ptr()):
+        sq, keep_q = sequence_in(queries, base)
+        sc, keep_c = sequence_in(candidates, base + split)
+        got = np.zeros_like(want)
+        status = lib.szs_levenshtein_distances(engine._handle, scope.handle, ct.byref(sq), ct.byref(sc), got.ctypes.data,
+                                               5, ct.byref(message))
+        assert status == 0 and np.array_equal(got, want)
+    lib.szs_unified_free(managed, len(blob))
+
 
 @pytest.mark.parametrize("seed", range(12))
 def test_randomized_differential(seed, scope):
