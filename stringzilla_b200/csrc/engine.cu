@@ -817,6 +817,15 @@ static Failure ensure_events(Engine &engine, int device) {
     return ok();
 }
 
+/** Strided 2-D copy of `rows` x `width` bytes that degenerates to ONE linear copy when both sides are dense: the copy
+ *  engine pays per row, and a score matrix has thousands of short rows. */
+static cudaError_t copy_rows(void *destination, size_t destination_pitch, void const *source, size_t source_pitch,
+                             size_t width, size_t rows, cudaMemcpyKind kind, cudaStream_t stream) {
+    if (destination_pitch == width && source_pitch == width)
+        return cudaMemcpyAsync(destination, source, width * rows, kind, stream);
+    return cudaMemcpy2DAsync(destination, destination_pitch, source, source_pitch, width, rows, kind, stream);
+}
+
 /** Grid of a grid-stride helper kernel: enough blocks for `items`, capped at a few waves of the device. */
 static int helper_grid(uint64_t items, int per_block, int device_sms, int waves) {
     return (int)std::max<uint64_t>(1, std::min<uint64_t>((items + per_block - 1) / per_block, (uint64_t)device_sms * waves));
@@ -1611,12 +1620,12 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
     bool const through_pinned = results_kind == MemoryKind::kPageable && home_bytes <= kPinnedDownloadLimit;
     if (through_pinned) {
         SZB_CUDA(engine.download.reserve(home_bytes));
-        SZB_CUDA(cudaMemcpy2DAsync(engine.download.ptr, home_columns * sizeof(int64_t), home, home_pitch,
-                                   home_columns * sizeof(int64_t), home_rows, cudaMemcpyDeviceToHost, stream));
+        SZB_CUDA(copy_rows(engine.download.ptr, home_columns * sizeof(int64_t), home, home_pitch,
+                           home_columns * sizeof(int64_t), home_rows, cudaMemcpyDeviceToHost, stream));
     }
     else {
-        SZB_CUDA(cudaMemcpy2DAsync(destination, stride * sizeof(int64_t), home, home_pitch,
-                                   home_columns * sizeof(int64_t), home_rows, cudaMemcpyDefault, stream));
+        SZB_CUDA(copy_rows(destination, stride * sizeof(int64_t), home, home_pitch, home_columns * sizeof(int64_t),
+                           home_rows, cudaMemcpyDefault, stream));
     }
     if (results_kind != MemoryKind::kDevice) stats.d2h_bytes += home_bytes;
     SZB_CUDA(cudaEventRecord(engine.events[3], stream));
@@ -1969,6 +1978,13 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
     if (scope.kind == Scope::kCpu) return fail(sz_device_code_mismatch_k, "GPU engine cannot run on a CPU device scope");
     if (Failure failure = scope.ensure_stream()) return failure;
     cudaStream_t const stream = scope.stream;
+    Trace trace; // SZB200_TRACE=1: host-side marks of the exchange on rank 0 (with a stream sync before each mark)
+    trace.enabled = trace.enabled && communicator.rank == 0;
+    auto mark = [&](char const *what) {
+        if (!trace.enabled) return;
+        cudaStreamSynchronize(stream);
+        trace.mark(what);
+    };
     bool const root = communicator.rank == 0;
     int const world = communicator.world;
     SZB_CUDA(communicator.header.reserve(kHeaderWords * sizeof(uint64_t)));
@@ -2038,7 +2054,9 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
             SZB_CUDA(cudaMemcpyAsync(payload + at_c_bytes, (char const *)candidates->data + c_first, bytes_c, cudaMemcpyDefault, stream));
         }
     }
+    mark("exchange: header broadcast and inputs packed");
     SZB_NCCL(nccl.Broadcast(payload, payload, payload_bytes, ncclUint8, 0, communicator.comm, stream));
+    mark("exchange: payload broadcast");
     if (!root) {
         communicator.q_offsets.resize(n_q + 1);
         SZB_CUDA(cudaMemcpyAsync(communicator.q_offsets.data(), payload, (n_q + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
@@ -2068,6 +2086,7 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
     if (n_q && columns)
         if (Failure failure = cross(engine, scope, q, c, slab, columns, begin, end, whole, root ? 0 : begin)) return failure;
 
+    mark("exchange: own rows scored");
     // 3. One gather of the slabs (rows x columns of int64, contiguous on both ends).
     if (world > 1 && columns) {
         SZB_NCCL(nccl.GroupStart());
@@ -2083,6 +2102,7 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
             SZB_NCCL(nccl.Send(slab, (end - begin) * columns * sizeof(int64_t), ncclUint8, 0, communicator.comm, stream));
         SZB_NCCL(nccl.GroupEnd());
     }
+    mark("exchange: slabs gathered");
     if (root && n_q && columns) {
         if (!results) return fail(sz_unexpected_dimensions_k, "Results pointer is null");
         if (stride < columns) return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
@@ -2091,10 +2111,11 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
             mirror_lower_kernel<<<helper_grid(n_q * n_q, 256, sms, 16), 256, 0, stream>>>(slab, n_q, columns);
             SZB_CUDA(cudaGetLastError());
         }
-        SZB_CUDA(cudaMemcpy2DAsync(results, stride * sizeof(int64_t), slab, columns * sizeof(int64_t), columns * sizeof(int64_t),
-                                   (size_t)n_q, cudaMemcpyDefault, stream));
+        SZB_CUDA(copy_rows(results, stride * sizeof(int64_t), slab, columns * sizeof(int64_t), columns * sizeof(int64_t),
+                           (size_t)n_q, cudaMemcpyDefault, stream));
     }
     SZB_CUDA(cudaStreamSynchronize(stream));
+    mark("exchange: matrix home");
     return ok();
 }
 
