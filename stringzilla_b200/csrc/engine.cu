@@ -1252,6 +1252,29 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     }
     for (size_t c = 0; c < n_candidates; ++c) cells_total += (uint64_t)candidate_length((uint32_t)c) * query_bytes_in_rows;
 
+    // Every (family, strip width) is a persistent launch of its own with a ragged end of its own (launches cannot share
+    // an SM): a launch with less than about a millisecond of work is folded into the next wider one of its family —
+    // a few padded columns cost less than another tail. Matters for strong-scaled shards (c4 on 8 GPUs: 9 launches of
+    // 1-3 ms each) much more than for whole tiles.
+    {
+        constexpr uint64_t min_launch_cells = 6000000000ull;
+        for (int family = 0; family < kFamilyCount; ++family) {
+            uint64_t cells[kStripCount] = {0};
+            for (HostSlot const &host : host_slots)
+                if (host.family == family)
+                    cells[host.shape.strip_index] += ((uint64_t)host.slot.len0 + host.slot.len1) * query_bytes_in_rows;
+            for (int strip = 0; strip + 1 < kStripCount; ++strip) {
+                if (!cells[strip] || cells[strip] >= min_launch_cells) continue;
+                int wider = -1;
+                for (int candidate = strip + 1; candidate < kStripCount && wider < 0; ++candidate)
+                    if (cells[candidate] && kStrips[candidate] <= widest_strip(family)) wider = candidate;
+                if (wider < 0) continue;
+                for (HostSlot &host : host_slots)
+                    if (host.family == family && host.shape.strip_index == strip) host.shape.strip_index = wider;
+                cells[wider] += cells[strip], cells[strip] = 0;
+            }
+        }
+    }
     trace.mark("slots built");
     // 6. Jobs: every slot crossed with blocks of the query order; one launch per (family, strip width).
     std::vector<Job> &host_jobs = schedule.jobs;
