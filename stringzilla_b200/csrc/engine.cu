@@ -592,7 +592,11 @@ static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_sta
                 }
             };
             std::vector<std::thread> threads;
-            for (unsigned t = 0; t + 1 < n_threads; ++t) threads.emplace_back(worker);
+            try {
+                for (unsigned t = 0; t + 1 < n_threads; ++t) threads.emplace_back(worker);
+            }
+            catch (...) { // no helper threads to be had: the loop below copies every chunk itself
+            }
             cudaError_t error = cudaSuccess;
             for (uint64_t i = 0; i < n_chunks; ++i) {
                 while (!done[i].load(std::memory_order_acquire)) {
@@ -2515,7 +2519,12 @@ SZS_B200_API sz_status_t szs_b200_device_group_init(sz_size_t const *gpu_devices
         scope->kind = Scope::kGpu, scope->cpu_cores = 0, scope->gpu_device = (int)device;
         made->scopes.push_back(std::move(scope));
     }
-    made->start();
+    try {
+        made->start();
+    }
+    catch (...) {
+        return szb::report(szb::fail(sz_bad_alloc_k, "Failed to start the device group's host threads"), error_message);
+    }
     *group = made.release();
     return szb::report(szb::ok(), error_message);
 }
