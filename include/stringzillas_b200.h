@@ -375,7 +375,9 @@ SZS_B200_API void szs_b200_comm_free(szs_b200_comm_t comm);
  *  managed or device memory) and the result matrix; the other ranks pass NULL for all three. ONE NCCL broadcast of the
  *  packed inputs (after a 64-byte header), row-sharded scoring, ONE grouped send/recv gather of the int64 score slabs
  *  to rank 0, which copies the whole matrix into `results`. Every (query, candidate) pair is independent, so nothing
- *  crosses GPUs during the DP itself. */
+ *  crosses GPUs during the DP itself. Arguments rank 0 rejects (null or decreasing offsets, a missing result matrix, a
+ *  stride below the candidate count) travel in the header: every rank returns that status instead of waiting in the
+ *  broadcast. */
 SZS_B200_API sz_status_t szs_b200_comm_scores_u64tape(int family, void *engine, szs_device_scope_t device,
                                                       szs_b200_comm_t comm, sz_sequence_u64tape_t const *queries,
                                                       sz_sequence_u64tape_t const *candidates, void *results,

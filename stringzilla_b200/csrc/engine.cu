@@ -2020,8 +2020,11 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
 
     // 1. Rank 0 packs both tapes into one message: offsets (relative, 64-bit) first, then the bytes.
     uint64_t n_q = 0, n_c = 0, bytes_q = 0, bytes_c = 0, symmetric = 0, q_first = 0, c_first = 0;
+    // Whatever rank 0 finds wrong with its arguments travels in the header: the other ranks are already waiting in the
+    // broadcast, and a rank that returned early would leave them there.
+    Failure rejected;
     if (root) {
-        if (!queries) return fail(sz_status_unknown_k, "Rank 0 must pass the queries");
+        if (!queries) rejected = fail(sz_status_unknown_k, "Rank 0 must pass the queries");
         symmetric = candidates == nullptr;
         auto measure = [](sz_sequence_u64tape_t const *tape, std::vector<uint64_t> &relative, uint64_t &bytes,
                           uint64_t &first) -> Failure {
@@ -2044,14 +2047,22 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
             bytes = relative[count], first = offsets[0];
             return ok();
         };
-        n_q = queries->count;
-        if (Failure failure = measure(queries, communicator.q_offsets, bytes_q, q_first)) return failure;
-        if (!symmetric) {
-            n_c = candidates->count;
-            if (Failure failure = measure(candidates, communicator.c_offsets, bytes_c, c_first)) return failure;
+        if (!rejected) {
+            n_q = queries->count;
+            rejected = measure(queries, communicator.q_offsets, bytes_q, q_first);
         }
+        if (!rejected && !symmetric) {
+            n_c = candidates->count;
+            rejected = measure(candidates, communicator.c_offsets, bytes_c, c_first);
+        }
+        if (!rejected && n_q && (symmetric ? n_q : n_c)) {
+            if (!results) rejected = fail(sz_unexpected_dimensions_k, "Results pointer is null");
+            else if (stride < (symmetric ? n_q : n_c))
+                rejected = fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
+        }
+        if (rejected) n_q = n_c = bytes_q = bytes_c = 0;
         header[0] = kHeaderMagic, header[1] = n_q, header[2] = n_c, header[3] = bytes_q, header[4] = bytes_c;
-        header[5] = symmetric, header[6] = header[7] = 0;
+        header[5] = symmetric, header[6] = (uint64_t)(int64_t)rejected.status, header[7] = 0;
         SZB_CUDA(cudaMemcpyAsync(communicator.header.ptr, header, kHeaderWords * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
     }
     SZB_NCCL(nccl.Broadcast(communicator.header.ptr, communicator.header.ptr, kHeaderWords * sizeof(uint64_t), ncclUint8, 0,
@@ -2061,6 +2072,11 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
         SZB_CUDA(cudaStreamSynchronize(stream));
         if (header[0] != kHeaderMagic) return fail(sz_status_unknown_k, "Malformed exchange header");
         n_q = header[1], n_c = header[2], bytes_q = header[3], bytes_c = header[4], symmetric = header[5];
+        if (header[6]) return fail((sz_status_t)(int64_t)header[6], "Rank 0 rejected its inputs");
+    }
+    else if (rejected) {
+        SZB_CUDA(cudaStreamSynchronize(stream)); // the header has left before this rank does
+        return rejected;
     }
     size_t const offsets_bytes = (size_t)((n_q + 1) + (symmetric ? 0 : n_c + 1)) * sizeof(uint64_t);
     size_t const at_q_bytes = (offsets_bytes + 15) & ~(size_t)15;

@@ -121,6 +121,16 @@ def test_communicator_of_one_rank():
         candidates = support.random_strings(rng, 11, 0, 200, alphabet)
         assert np.array_equal(engine.communicate(communicator, scope, queries, candidates), oracle(queries, candidates)), name
         assert np.array_equal(engine.communicate(communicator, scope, queries, None), oracle(queries, None)), name
+    # What rank 0 rejects travels in the exchange header (every rank returns it instead of waiting in a collective),
+    # and the communicator stays usable.
+    name, engine, alphabet, oracle = _engines()[0]
+    queries = support.random_strings(rng, 5, 1, 50, alphabet)
+    candidates = support.random_strings(rng, 4, 1, 50, alphabet)
+    too_narrow = np.zeros((5, 3), dtype=np.uint64)
+    with pytest.raises(szb.SimilarityError) as refusal:
+        engine.communicate(communicator, scope, queries, candidates, out=too_narrow)
+    assert refusal.value.status == -15 and "stride" in str(refusal.value)  # sz_unexpected_dimensions_k
+    assert np.array_equal(engine.communicate(communicator, scope, queries, candidates), oracle(queries, candidates))
 
 
 def _two_rank_worker(rank: int, id_path: str, seed: int):
@@ -150,6 +160,14 @@ def _two_rank_worker(rank: int, id_path: str, seed: int):
                 assert np.array_equal(got, oracle(queries, None if symmetric else candidates)), (name, symmetric)
             else:
                 assert got is None
+    # Rank 0's rejection of its own arguments reaches rank 1 through the header: both return it, nobody waits.
+    engine = _engines()[0][1]
+    with pytest.raises(szb.SimilarityError) as refusal:
+        if rank == 0:
+            engine.communicate(communicator, scope, queries, candidates, out=np.zeros((len(queries), 1), dtype=np.uint64))
+        else:
+            engine.communicate(communicator, scope)
+    assert refusal.value.status == -15  # sz_unexpected_dimensions_k
     # The threaded orchestrator over two real devices, from rank 0's process alone.
     if rank == 0:
         group = szb.DeviceGroup([0, 1])
