@@ -1059,6 +1059,20 @@ struct Schedule {
     uint64_t cells_total = 0, cells_u16 = 0, cells_myers = 0;
 };
 
+/** Bit-parallel launches of one call (different words per lane) share the SMs' resident CTA slots in proportion to
+ *  their work and run side by side from the start, instead of each asking for every slot and queueing behind the other:
+ *  a sweep is a coarse unit (c2: 2.7 per warp over both launches), so two launches in turn mean two ragged ends at a
+ *  third of the occupancy, side by side they mean one. */
+#ifndef SZB_SHARE_RESIDENT_SLOTS
+#define SZB_SHARE_RESIDENT_SLOTS 0
+#endif
+
+/** EXPERIMENT, off by default: bit-parallel shapes are widened (more lanes, fewer words per lane: finer sweeps) until a
+ *  call holds at least this many sweeps per resident warp. */
+#ifndef SZB_MYERS_MIN_SWEEPS_PER_WARP
+#define SZB_MYERS_MIN_SWEEPS_PER_WARP 0
+#endif
+
 /** Multi-pass slots park one boundary column per query row in per-CTA scratch: a job's block is cut so that its
  *  scratch stays below this many 32-bit words (16 MB), whatever the row count of the call. */
 constexpr uint64_t kScratchWordsPerJob = 4ull << 20;
@@ -1122,6 +1136,10 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     uint64_t const n_pairs = (uint64_t)n_rows * n_candidates;
     uint32_t latency_lanes = 1;
     while (latency_lanes < 32 && n_pairs * latency_lanes * 2 <= device_warps * 32) latency_lanes *= 2;
+    uint32_t myers_min_lanes = latency_lanes;
+    if (SZB_MYERS_MIN_SWEEPS_PER_WARP)
+        while (myers_min_lanes < 32 && n_pairs * myers_min_lanes < (uint64_t)SZB_MYERS_MIN_SWEEPS_PER_WARP * 2 * device_warps * 32)
+            myers_min_lanes *= 2;
 
     // 5a. Unit-cost Levenshtein over a compact alphabet: candidates the bit-parallel kernel covers leave the DP tiers.
     std::vector<MyersLaunch> &myers_launches = schedule.myers_launches;
@@ -1153,7 +1171,7 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
             uint32_t const c = by_length[i], length = candidate_length(c);
             // Candidates arrive sorted by length: equal lengths are neighbours, so one remembered answer suffices.
             if (length != remembered_length) {
-                myers_shape_for_length(length, max_words, (int)latency_lanes, remembered_words, remembered_lanes);
+                myers_shape_for_length(length, max_words, (int)myers_min_lanes, remembered_words, remembered_lanes);
                 remembered_length = length;
             }
             int const words = remembered_words, lanes = remembered_lanes;
@@ -1544,14 +1562,44 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
         for (cudaStream_t side : engine.side_streams) SZB_CUDA(cudaStreamWaitEvent(side, engine.fork_event, 0));
     }
     {
+        int const warps = kThreads / 32;
+        auto table_bytes = [&](MyersLaunch const &launch) -> size_t {
+            return myers_rune_table     ? myers_rune_bytes(myers_rows)
+                   : myers_shared_table ? myers_shared_bytes(launch.words, myers_rows)
+                                        : (size_t)model.scoring.n_classes * 32 * launch.words * 4 * warps;
+        };
+        auto resident_ctas = [&](MyersLaunch const &launch) { return (!myers_shared_table && table_bytes(launch) * 2 <= 220 * 1024) ? 2 : 1; };
+        // Several bit-parallel launches running side by side (one stream each) share the resident CTA slots in proportion
+        // to their work — sweeps x steps x words — instead of each claiming all of them: see SZB_SHARE_RESIDENT_SLOTS.
+        std::vector<uint64_t> slot_share(myers_launches.size(), 0);
+        if (SZB_SHARE_RESIDENT_SLOTS && myers_launches.size() > 1 && n_launches <= (size_t)Engine::kSideStreams + 1) {
+            int const per_sm = resident_ctas(myers_launches[0]);
+            bool uniform = true;
+            std::vector<long double> weight(myers_launches.size(), 0);
+            long double total_weight = 0;
+            for (size_t l = 0; l < myers_launches.size(); ++l) {
+                uniform = uniform && resident_ctas(myers_launches[l]) == per_sm;
+                for (MyersCandidate const &member : myers_launches[l].members)
+                    weight[l] += (long double)member.rows * member.lanes * (myers_launches[l].words + 0.3L);
+                total_weight += weight[l];
+            }
+            if (uniform && total_weight > 0) {
+                uint64_t const slots = (uint64_t)device_sms * per_sm;
+                uint64_t granted = 0;
+                size_t heaviest = 0;
+                for (size_t l = 0; l < myers_launches.size(); ++l) {
+                    slot_share[l] = std::max<uint64_t>(1, (uint64_t)(slots * (weight[l] / total_weight)));
+                    granted += slot_share[l];
+                    if (weight[l] > weight[heaviest]) heaviest = l;
+                }
+                if (granted < slots) slot_share[heaviest] += slots - granted; // rounding leftovers
+            }
+        }
         size_t first = 0;
         for (size_t l = 0; l < myers_launches.size(); ++l) {
             MyersLaunch const &launch = myers_launches[l];
-            int const warps = kThreads / 32;
-            size_t const smem = myers_rune_table     ? myers_rune_bytes(myers_rows)
-                                : myers_shared_table ? myers_shared_bytes(launch.words, myers_rows)
-                                    : (size_t)model.scoring.n_classes * 32 * launch.words * 4 * warps;
-            int const ctas_per_sm = (!myers_shared_table && smem * 2 <= 220 * 1024) ? 2 : 1;
+            size_t const smem = table_bytes(launch);
+            int const ctas_per_sm = resident_ctas(launch);
             // Work units that pull tasks: warps (private tables) or whole CTAs (shared table).
             uint64_t const pullers = myers_shared_table ? (uint64_t)device_sms : (uint64_t)device_sms * ctas_per_sm * warps;
             uint32_t narrowest = 32;
@@ -1578,9 +1626,9 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
             args.stride = n_candidates;
             args.row_base = (uint32_t)row_begin;
             uint64_t const tasks = blocks * launch.members.size();
-            int const grid = myers_shared_table
-                                 ? (int)std::min<uint64_t>(tasks, (uint64_t)device_sms)
-                                 : (int)std::min<uint64_t>((tasks + warps - 1) / warps, (uint64_t)device_sms * ctas_per_sm);
+            uint64_t const resident = slot_share[l] ? slot_share[l] : (uint64_t)device_sms * ctas_per_sm;
+            int const grid = myers_shared_table ? (int)std::min<uint64_t>(tasks, resident)
+                                                : (int)std::min<uint64_t>((tasks + warps - 1) / warps, resident);
             int const table = myers_rune_table ? kMyersRuneTable : myers_shared_table ? kMyersSharedTable : kMyersPrivateTables;
             SZB_CUDA(launch_myers(launch.words, table, grid, kThreads, smem, next_stream(), args));
             stats.kernel_launches++;
