@@ -6,6 +6,12 @@
 
 #include <atomic>
 
+/** EXPERIMENT, off by default and not yet measured: every bit-parallel kernel asks for the same (largest) shared-memory
+ *  carve-out, so that CTAs of launches with different words per lane may share an SM. */
+#ifndef SZB_MYERS_ONE_CARVEOUT
+#define SZB_MYERS_ONE_CARVEOUT 0
+#endif
+
 namespace szb {
 
 template <int W, bool SHARED>
@@ -20,6 +26,10 @@ static cudaError_t launch_words(int grid, int threads, size_t smem, cudaStream_t
     if (!(configured.load(std::memory_order_acquire) & bit)) {
         cudaError_t status = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (status != cudaSuccess) return status;
+        if (SZB_MYERS_ONE_CARVEOUT) {
+            status = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (status != cudaSuccess) return status;
+        }
         configured.fetch_or(bit, std::memory_order_release);
     }
     kernel<<<grid, threads, smem, stream>>>(args);
