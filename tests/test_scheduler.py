@@ -137,3 +137,51 @@ def test_jobs_are_single_rounds_on_large_tiles():
                                                   distinct_bytes=20)
     check_invariants(q, c, assignment, partner, order, jobs)
     assert len(jobs) >= 148 * 16 and max(end - begin for _, begin, end in jobs.tolist()) == 16
+
+
+def _engine_zoo():
+    byte_to_class, table = scoring.blosum62()
+    return [
+        szb.LevenshteinDistances(),
+        szb.LevenshteinDistances(bit_parallel=False),
+        szb.LevenshteinDistances(1, 3, 3, 3),
+        szb.LevenshteinDistances(1, 3, 4, 2),
+        szb.LevenshteinDistances(0, 100, 100, 100),
+        szb.NeedlemanWunschScores(byte_to_class, table, open=-4, extend=-4),
+        szb.NeedlemanWunschScores(byte_to_class, table, open=-4, extend=-1),
+        szb.SmithWatermanScores(byte_to_class, table, open=-4, extend=-1),
+        szb.SmithWatermanScores(byte_to_class, table, open=-2, extend=1),
+    ]
+
+
+def _random_lengths(rng, count, longest, flavour):
+    if flavour == 0:
+        return rng.integers(0, longest + 1, size=count)
+    if flavour == 1:  # log-uniform, like the c4 tile
+        return np.exp(rng.uniform(0, np.log(longest + 1), size=count)).astype(np.int64)
+    if flavour == 2:  # a narrow band around one length, like c2
+        return rng.integers(max(0, longest - longest // 8), longest + 1, size=count)
+    lengths = rng.integers(0, longest + 1, size=count)  # many empty and equal strings
+    lengths[rng.random(count) < 0.4] = 0
+    lengths[rng.random(count) < 0.3] = longest
+    return lengths
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_calls_keep_the_schedule_invariants(seed):
+    """Randomised sweep over engines, length distributions, alphabets, device sizes and symmetric calls: the invariants of
+    `check_invariants` hold for every schedule the host builds (the scheduler is pure host code, no GPU involved)."""
+    rng = np.random.default_rng(1000 + seed)
+    engines = _engine_zoo()
+    engine = engines[seed % len(engines)]
+    n_queries = int(rng.choice([1, 2, 7, 33, 200, 1500]))
+    n_candidates = int(rng.choice([1, 3, 40, 250]))
+    longest = int(rng.choice([0, 1, 31, 300, 1100, 5000, 12000]))
+    flavour = int(rng.integers(0, 4))
+    distinct = int(rng.choice([1, 4, 24, 31, 32, 200]))
+    device_sms = int(rng.choice([1, 8, 148, 160]))
+    symmetric = bool(rng.integers(0, 3) == 0)
+    q = _random_lengths(rng, n_queries, longest, flavour)
+    c = None if symmetric else _random_lengths(rng, n_candidates, longest, int(rng.integers(0, 4)))
+    result = plan(engine, q, c, distinct_bytes=distinct, device_sms=device_sms)
+    check_invariants(*result, symmetric=symmetric and n_queries > 1)
