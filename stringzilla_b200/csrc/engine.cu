@@ -645,9 +645,9 @@ static Failure upload_raw(StagedSet &set, cudaStream_t stream, szs_b200_call_sta
     SZB_CUDA(cudaMemcpyAsync(set.gather_list.ptr, set.gather.ptr, pointer_bytes + offset_bytes, cudaMemcpyHostToDevice, stream));
     stats.h2d_bytes += pointer_bytes + offset_bytes;
     int const blocks = (int)std::min<size_t>((set.count + 7) / 8, 4096);
-    gather_strings_kernel<<<blocks, 256, 0, stream>>>((uint8_t const *const *)set.gather_list.ptr,
-                                                      (uint32_t const *)((char *)set.gather_list.ptr + pointer_bytes),
-                                                      (uint32_t)set.count, set.raw.as<uint8_t>());
+    SZB_LAUNCH(gather_strings_kernel, blocks, 256, 0, stream, (uint8_t const *const *)set.gather_list.ptr,
+               (uint32_t const *)((char *)set.gather_list.ptr + pointer_bytes), (uint32_t)set.count,
+               set.raw.as<uint8_t>());
     SZB_CUDA(cudaGetLastError());
     stats.kernel_launches++;
     return ok();
@@ -874,16 +874,16 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
             SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
             SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
             if (cs.total_bytes) {
-                byte_presence_kernel<<<2 * device_sms, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
-                                                                         engine.flags.as<uint32_t>());
+                SZB_LAUNCH(byte_presence_kernel, 2 * device_sms, 512, 0, stream, cs.raw.as<uint8_t>(), cs.total_bytes,
+                           engine.flags.as<uint32_t>());
                 SZB_CUDA(cudaGetLastError());
                 stats.kernel_launches++;
             }
             if (need_queries) {
                 SZB_CUDA(engine.query_flags.reserve(256 * sizeof(uint32_t)));
                 SZB_CUDA(cudaMemsetAsync(engine.query_flags.ptr, 0, 256 * sizeof(uint32_t), stream));
-                byte_presence_kernel<<<2 * device_sms, 512, 0, stream>>>(qs.raw.as<uint8_t>(), qs.total_bytes,
-                                                                         engine.query_flags.as<uint32_t>());
+                SZB_LAUNCH(byte_presence_kernel, 2 * device_sms, 512, 0, stream, qs.raw.as<uint8_t>(), qs.total_bytes,
+                           engine.query_flags.as<uint32_t>());
                 SZB_CUDA(cudaGetLastError());
                 stats.kernel_launches++;
                 SZB_CUDA(cudaMemcpyAsync(query_present, engine.query_flags.ptr, sizeof(query_present),
@@ -918,8 +918,8 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
         stats.h2d_bytes += (size_t)(count + 1) * sizeof(uint32_t);
         int const blocks = (int)((count + 127) / 128);
         if (count) {
-            utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
-                                                           count, set.rune_counts.as<uint32_t>(), nullptr, nullptr);
+            SZB_LAUNCH(utf8_decode_kernel, blocks, 128, 0, stream, set.raw.as<uint8_t>(),
+                       set.device_offsets.as<uint32_t>(), count, set.rune_counts.as<uint32_t>(), nullptr, nullptr);
             SZB_CUDA(cudaGetLastError());
             stats.kernel_launches++;
         }
@@ -941,9 +941,9 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
                                  cudaMemcpyHostToDevice, stream));
         SZB_CUDA(set.runes.reserve((running + 64) * sizeof(uint32_t)));
         if (count) {
-            utf8_decode_kernel<<<blocks, 128, 0, stream>>>(set.raw.as<uint8_t>(), set.device_offsets.as<uint32_t>(),
-                                                           count, nullptr, set.rune_offsets.as<uint32_t>(),
-                                                           set.runes.as<uint32_t>());
+            SZB_LAUNCH(utf8_decode_kernel, blocks, 128, 0, stream, set.raw.as<uint8_t>(),
+                       set.device_offsets.as<uint32_t>(), count, nullptr, set.rune_offsets.as<uint32_t>(),
+                       set.runes.as<uint32_t>());
             SZB_CUDA(cudaGetLastError());
             stats.kernel_launches++;
         }
@@ -970,15 +970,16 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
     if (Failure failure = for_each_side([&](StagedSet &set) -> Failure {
             uint64_t const n = set.offsets[set.count];
             if (!n) return ok();
-            rune_insert_kernel<<<helper_grid(n, 256, device_sms, 8), 256, 0, stream>>>(
-                set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(), engine.rune_state.as<uint32_t>());
+            SZB_LAUNCH(rune_insert_kernel, helper_grid(n, 256, device_sms, 8), 256, 0, stream,
+                       set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(),
+                       engine.rune_state.as<uint32_t>());
             SZB_CUDA(cudaGetLastError());
             stats.kernel_launches++;
             return ok();
         }))
         return failure;
-    rune_rank_kernel<<<1, 1024, 0, stream>>>(engine.rune_table.as<uint32_t>(), engine.rune_ranks.as<uint32_t>(),
-                                             engine.rune_state.as<uint32_t>());
+    SZB_LAUNCH(rune_rank_kernel, 1, 1024, 0, stream, engine.rune_table.as<uint32_t>(),
+               engine.rune_ranks.as<uint32_t>(), engine.rune_state.as<uint32_t>());
     SZB_CUDA(cudaGetLastError());
     stats.kernel_launches++;
     uint32_t rune_state[2] = {0, 0};
@@ -991,9 +992,9 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
                 // The id stream overwrites the staged UTF-8 bytes (never longer than them); the symbol offsets (already
                 // in `set.offsets`) become the byte offsets of the byte-level problem.
                 if (n) {
-                    rune_map_kernel<<<helper_grid(n, 256, device_sms, 8), 256, 0, stream>>>(
-                        set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(), engine.rune_ranks.as<uint32_t>(),
-                        set.raw.as<uint8_t>());
+                    SZB_LAUNCH(rune_map_kernel, helper_grid(n, 256, device_sms, 8), 256, 0, stream,
+                               set.runes.as<uint32_t>(), n, engine.rune_table.as<uint32_t>(),
+                               engine.rune_ranks.as<uint32_t>(), set.raw.as<uint8_t>());
                     SZB_CUDA(cudaGetLastError());
                     stats.kernel_launches++;
                 }
@@ -1007,8 +1008,8 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
         SZB_CUDA(engine.flags.reserve(256 * sizeof(uint32_t)));
         SZB_CUDA(cudaMemsetAsync(engine.flags.ptr, 0, 256 * sizeof(uint32_t), stream));
         if (cs.total_bytes) {
-            byte_presence_kernel<<<2 * device_sms, 512, 0, stream>>>(cs.raw.as<uint8_t>(), cs.total_bytes,
-                                                                     engine.flags.as<uint32_t>());
+            SZB_LAUNCH(byte_presence_kernel, 2 * device_sms, 512, 0, stream, cs.raw.as<uint8_t>(), cs.total_bytes,
+                       engine.flags.as<uint32_t>());
             SZB_CUDA(cudaGetLastError());
             stats.kernel_launches++;
         }
@@ -1527,8 +1528,9 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
         auto map_set = [&](StagedSet &set) -> Failure {
             if (!set.total_bytes) return ok();
             uint64_t const vectors = (set.total_bytes + 15) / 16;
-            map_classes_kernel<<<helper_grid(vectors, 256, device_sms, 8), 256, 0, stream>>>(
-                set.raw.as<uint8_t>(), set.classes.as<uint8_t>(), set.total_bytes, (uint8_t const *)(device + at_lut));
+            SZB_LAUNCH(map_classes_kernel, helper_grid(vectors, 256, device_sms, 8), 256, 0, stream,
+                       set.raw.as<uint8_t>(), set.classes.as<uint8_t>(), set.total_bytes,
+                       (uint8_t const *)(device + at_lut));
             SZB_CUDA(cudaGetLastError());
             stats.kernel_launches++;
             return ok();
@@ -1666,18 +1668,19 @@ static Failure cross_unguarded(Engine &engine, Scope &scope, cudaStream_t stream
         uint64_t const total = (uint64_t)n_queries * n_queries;
         int const blocks = helper_grid(total, 256, device_sms, 16);
         if (triangle)
-            mirror_ranked_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates,
-                                                             (uint32_t const *)(device + at_position));
+            SZB_LAUNCH(mirror_ranked_kernel, blocks, 256, 0, stream, engine.results.as<int64_t>(), n_queries,
+                       n_candidates, (uint32_t const *)(device + at_position));
         else
-            mirror_lower_kernel<<<blocks, 256, 0, stream>>>(engine.results.as<int64_t>(), n_queries, n_candidates);
+            SZB_LAUNCH(mirror_lower_kernel, blocks, 256, 0, stream, engine.results.as<int64_t>(), n_queries,
+                       n_candidates);
         SZB_CUDA(cudaGetLastError());
         stats.kernel_launches++;
     }
     int64_t const *home = engine.results.as<int64_t>();
     if (swapped) {
         uint64_t const total = (uint64_t)caller_rows * caller_columns;
-        transpose_results_kernel<<<helper_grid(total, 256, device_sms, 16), 256, 0, stream>>>(
-            engine.results.as<int64_t>(), engine.results_home.as<int64_t>(), caller_rows, caller_columns);
+        SZB_LAUNCH(transpose_results_kernel, helper_grid(total, 256, device_sms, 16), 256, 0, stream,
+                   engine.results.as<int64_t>(), engine.results_home.as<int64_t>(), caller_rows, caller_columns);
         SZB_CUDA(cudaGetLastError());
         stats.kernel_launches++;
         home = engine.results_home.as<int64_t>();
@@ -1949,8 +1952,8 @@ static Failure sharded_cross(Engine &engine, DeviceGroup &group, sz_sequence_u64
             Scope &scope = *group.scopes[0];
             SZB_CUDA(cudaSetDevice(scope.gpu_device));
             int const sms = std::max(1, device_facts(scope.gpu_device).sms);
-            mirror_lower_kernel<<<helper_grid((uint64_t)call.n * call.n, 256, sms, 16), 256, 0, scope.stream>>>(
-                (int64_t *)results, call.n, stride);
+            SZB_LAUNCH(mirror_lower_kernel, helper_grid((uint64_t)call.n * call.n, 256, sms, 16), 256, 0, scope.stream,
+                       (int64_t *)results, call.n, stride);
             SZB_CUDA(cudaGetLastError());
             SZB_CUDA(cudaStreamSynchronize(scope.stream));
         }
@@ -2199,7 +2202,7 @@ static Failure communicator_cross(Engine &engine, Scope &scope, Communicator &co
         if (stride < columns) return fail(sz_unexpected_dimensions_k, "Results row stride is smaller than the candidates count");
         if (symmetric && world > 1 && n_q > 1) {
             int const sms = std::max(1, device_facts(scope.gpu_device).sms);
-            mirror_lower_kernel<<<helper_grid(n_q * n_q, 256, sms, 16), 256, 0, stream>>>(slab, n_q, columns);
+            SZB_LAUNCH(mirror_lower_kernel, helper_grid(n_q * n_q, 256, sms, 16), 256, 0, stream, slab, n_q, columns);
             SZB_CUDA(cudaGetLastError());
         }
         SZB_CUDA(copy_rows(results, stride * sizeof(int64_t), slab, columns * sizeof(int64_t), columns * sizeof(int64_t),

@@ -27,7 +27,7 @@ static cudaError_t launch_strip(int grid, size_t smem, cudaStream_t stream, Kern
         if (status != cudaSuccess) return status;
         configured.fetch_or(bit, std::memory_order_release);
     }
-    kernel<<<grid, kThreads, smem, stream>>>(args);
+    SZB_LAUNCH(kernel, grid, kThreads, smem, stream, args);
     return cudaGetLastError();
 }
 

@@ -44,8 +44,7 @@
  *      and UTF-32 symbol streams (compare mode: the substitution is a symbol comparison instead of a profile lookup).
  */
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "ptx.cuh"
 
 /** Smith-Waterman affine, variant: cells stored as H (not H + open), the `+ open` of both gap tracks formed by adds off
  *  the dependency chain (4 FMA-pipe adds per cell pair instead of 3, a 2-op instead of a 3-op chain per cell). */
@@ -147,42 +146,9 @@ __device__ __forceinline__ int profile_term(int8_t const *sub, int a, int b, boo
     else { return valid ? s : -(1 << 28); }
 }
 
-/** A 32-bit add that is guaranteed to issue on the FMA pipe (IMAD with a multiplier the compiler cannot fold): the
- *  packed recurrences saturate the ALU pipe with DPX instructions, and ptxas otherwise turns part of the plain adds
- *  into ALU-pipe VIADDs. */
-__device__ __forceinline__ uint32_t add_on_fma_pipe(uint32_t a, uint32_t b, uint32_t one) {
-    uint32_t sum;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(a), "r"(one), "r"(b));
-    return sum;
-}
-
-/* ---- TMA (bulk asynchronous copy) of the slot's candidate bytes into shared memory, completion on an mbarrier ------ */
-
-/** Bytes reserved per staged candidate window: the widest pass (40 x 32 columns) plus the 16-byte alignment slack at
- *  both ends. */
+/** Bytes reserved per staged candidate window (the slot's candidate bytes reach shared memory through the TMA engine,
+ *  `bulk_copy_to_shared` in ptx.cuh): the widest pass (40 x 32 columns) plus the 16-byte alignment slack at both ends. */
 constexpr int kStageBytes = 40 * 32 + 32;
-
-__device__ __forceinline__ void mbarrier_init(uint32_t barrier, uint32_t arrivals) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barrier), "r"(arrivals) : "memory");
-}
-__device__ __forceinline__ void mbarrier_expect_bytes(uint32_t barrier, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barrier), "r"(bytes) : "memory");
-}
-/** One 1-D bulk copy global -> shared (`cp.async.bulk`, the TMA engine without a tensor map: these are byte runs).
- *  Source, destination and size are multiples of 16 bytes. */
-__device__ __forceinline__ void bulk_copy_to_shared(uint32_t destination, void const *source, uint32_t bytes, uint32_t barrier) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(destination),
-                 "l"(source), "r"(bytes), "r"(barrier)
-                 : "memory");
-}
-__device__ __forceinline__ void mbarrier_wait(uint32_t barrier, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred arrived;\n\t"
-                 "SZB_WAIT_FOR_BYTES:\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 arrived, [%0], %1;\n\t"
-                 "@!arrived bra SZB_WAIT_FOR_BYTES;\n\t}" ::"r"(barrier),
-                 "r"(parity)
-                 : "memory");
-}
 
 /** Score of aligning `len` characters against nothing: serial.hpp:165-177 of the reference. */
 template <int FAM>
@@ -345,7 +311,7 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
         }
     }
     // Shared-window byte address of this lane's slot in profile row 0; a row is K / 4 vectors of 32 slots x 16 bytes.
-    uint32_t const strip_address = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)gl * 16u;
+    uint32_t const strip_address = shared_window_address(prof) + (uint32_t)gl * 16u;
     constexpr uint32_t row_bytes = (uint32_t)K * 32u * 4u;
 
     // Sub-strip B's inputs: the row class and validity sub-strip A had one step ago, and the last cell of sub-strip A
@@ -417,19 +383,16 @@ __device__ __forceinline__ void sweep_batch(KernelArgs const &args, SweepConstan
     // updated in place and nothing has to be moved aside.
     auto first_sum = [&](int k, uint32_t diagonal, uint32_t row_address, uint32_t a) -> uint32_t {
         if (!compare) {
-            uint32_t term; // column k's term sits in the last slot of the vector before it (column 0: of the last vector)
+            // Column k's term sits in the last slot of the vector before it (column 0: of the last vector).
             uint32_t const slot_before = (uint32_t)((k == 0 ? VECS : k / 4) - 1) * 512u + 12u;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(term) : "r"(row_address + slot_before));
-            return add(diagonal, term);
+            return add(diagonal, load_shared_word(row_address + slot_before));
         }
         return add(diagonal, compared(k, a));
     };
     auto vector = [&](int v, uint32_t row_address, uint32_t a, uint32_t &t_carry, uint32_t &l, uint32_t &e) {
         uint32_t p[4];
         if (!compare) {
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(p[0]), "=r"(p[1]), "=r"(p[2]), "=r"(p[3])
-                         : "r"(row_address + (uint32_t)v * 512u));
+            load_shared_quad(row_address + (uint32_t)v * 512u, p[0], p[1], p[2], p[3]);
         }
         else {
 #pragma unroll
@@ -602,8 +565,8 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     int8_t *const sub = (int8_t *)(smem + 4);  // 1024 B
     uint8_t *const stage = (uint8_t *)(smem + 4 + 256); // 2 x kStageBytes: the slot's candidate bytes of this pass
     uint32_t *const prof = smem + 4 + 256 + 2 * kStageBytes / 4; // [n_classes][K / 4][32 slots][4]; unused in compare mode
-    uint32_t const barrier = (uint32_t)__cvta_generic_to_shared(ctl + 2);
-    uint32_t const stage_address = (uint32_t)__cvta_generic_to_shared(stage);
+    uint32_t const barrier = shared_window_address(ctl + 2);
+    uint32_t const stage_address = shared_window_address(stage);
     uint32_t barrier_parity = 0;
 
     SweepConstants sc;
@@ -623,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     for (int i = threadIdx.x; i < 256; i += kThreads) ((uint32_t *)sub)[i] = ((uint32_t const *)sc_global->sub)[i];
     if (threadIdx.x == 0) {
         mbarrier_init(barrier, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbarrier_init_fence();
     }
     int const lane = threadIdx.x & 31;
 

@@ -32,7 +32,7 @@ static cudaError_t launch_words(int grid, int threads, size_t smem, cudaStream_t
         }
         configured.fetch_or(bit, std::memory_order_release);
     }
-    kernel<<<grid, threads, smem, stream>>>(args);
+    SZB_LAUNCH(kernel, grid, threads, smem, stream, args);
     return cudaGetLastError();
 }
 
@@ -66,7 +66,7 @@ static cudaError_t launch_runes(int grid, int threads, size_t smem, cudaStream_t
         if (status != cudaSuccess) return status;
         configured.fetch_or(bit, std::memory_order_release);
     }
-    myers_rune_kernel<1><<<grid, threads, smem, stream>>>(args);
+    SZB_LAUNCH(myers_rune_kernel<1>, grid, threads, smem, stream, args);
     return cudaGetLastError();
 }
 
