@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) wavefront_kernel(KernelArgs const
     constexpr bool packed = traits::packed;
     static_assert(K % 4 == 0, "strips are read as 16-byte vectors");
 
-    extern __shared__ __align__(16) uint32_t smem[];
+    SZB_DYNAMIC_SHARED(smem);
     Scoring const *const sc_global = args.scoring;
     int const n_classes = sc_global->n_classes;
     uint32_t *const ctl = smem;                // [0] job index, [1] next batch, [2..3] the mbarrier of the TMA copies

@@ -15,6 +15,9 @@
 /** `kernel<<<grid, threads, shared_bytes, stream>>>(arguments...)`. */
 #define SZB_LAUNCH(kernel, grid, threads, shared_bytes, stream, ...) kernel<<<(grid), (threads), (shared_bytes), (stream)>>>(__VA_ARGS__)
 
+/** The CTA's dynamic shared memory as an array of 32-bit words called `name`. */
+#define SZB_DYNAMIC_SHARED(name) extern __shared__ __align__(16) uint32_t name[]
+
 namespace szb {
 
 /* ---- Integer arithmetic pinned to the FMA pipe ------------------------------------------------------------------- */

@@ -333,9 +333,18 @@ def test_every_input_layout_of_the_abi(scope):
                                            5, ct.byref(message))
     assert status == 0 and np.array_equal(got, want)
 
-    # Callback sequences whose strings live in managed memory (the reference bench's `unified_alloc` tokens) and in device
-    # memory: the strings are gathered on the device from an uploaded pointer list, the host never reads them.
-    import torch
+
+@pytest.mark.parametrize("memory", ["unified_memory", "cuda_memory"])
+def test_callback_sequences_outside_host_memory(memory, scope):
+    """Callback sequences whose strings live in managed memory (the reference bench's `unified_alloc` tokens) and in device
+    memory: the strings are gathered on the device from an uploaded pointer list, the host never reads them."""
+    rng = np.random.default_rng(19)
+    queries = support.random_strings(rng, 6, 0, 90, support.DNA)
+    candidates = support.random_strings(rng, 5, 0, 90, support.DNA)
+    want = support.oracle_levenshtein(queries, candidates)
+    lib = _abi.bind()
+    engine = szb.LevenshteinDistances()
+    message = ct.c_char_p()
 
     def sequence_in(strings, base_address):
         offsets = np.concatenate([[0], np.cumsum([len(s) for s in strings])]).astype(np.int64)
@@ -345,17 +354,22 @@ def test_every_input_layout_of_the_abi(scope):
 
     blob = b"".join(queries) + b"".join(candidates)
     split = sum(len(s) for s in queries)
-    managed = lib.szs_unified_alloc(len(blob))
-    ct.memmove(managed, blob, len(blob))
-    device_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
-    for base in (managed, device_blob.data_ptr()):
-        sq, keep_q = sequence_in(queries, base)
-        sc, keep_c = sequence_in(candidates, base + split)
-        got = np.zeros_like(want)
-        status = lib.szs_levenshtein_distances(engine._handle, scope.handle, ct.byref(sq), ct.byref(sc), got.ctypes.data,
-                                               5, ct.byref(message))
-        assert status == 0 and np.array_equal(got, want)
-    lib.szs_unified_free(managed, len(blob))
+    if memory == "unified_memory":
+        base = lib.szs_unified_alloc(len(blob))
+        ct.memmove(base, blob, len(blob))
+    else:
+        import torch
+
+        device_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+        base = device_blob.data_ptr()
+    sq, keep_q = sequence_in(queries, base)
+    sc, keep_c = sequence_in(candidates, base + split)
+    got = np.zeros_like(want)
+    status = lib.szs_levenshtein_distances(engine._handle, scope.handle, ct.byref(sq), ct.byref(sc), got.ctypes.data,
+                                           5, ct.byref(message))
+    assert status == 0 and np.array_equal(got, want)
+    if memory == "unified_memory":
+        lib.szs_unified_free(base, len(blob))
 
 
 @pytest.mark.parametrize("seed", range(12))
