@@ -30,10 +30,6 @@ def sources() -> list[Path]:
         [HERE / "simt.cpp", ROOT / "include" / "stringzillas_b200.h", Path(__file__)]
 
 
-def up_to_date() -> bool:
-    return LIBRARY.exists() and LIBRARY.stat().st_mtime >= max(path.stat().st_mtime for path in sources())
-
-
 def link_tree() -> Path:
     """`_build/tree/stringzilla_b200/csrc/*` -> the product sources (but the emulator's ptx.cuh), `_build/tree/include`."""
     tree = BUILD / "tree"
@@ -54,12 +50,17 @@ def link_tree() -> Path:
     return csrc
 
 
-def build(verbose: bool = False) -> Path:
-    if up_to_date():
-        return LIBRARY
+def build(verbose: bool = False, sanitize: bool = False) -> Path:
+    """`sanitize=True` builds `libstringzillas_b200_emulated_asan.so` with AddressSanitizer: exact-size device allocations,
+    the unrequested part of shared memory poisoned (run the tests with the sanitizer's runtime preloaded, see
+    tools/emulator_memcheck.sh)."""
+    library = LIBRARY.with_name("libstringzillas_b200_emulated_asan.so") if sanitize else LIBRARY
+    if library.exists() and library.stat().st_mtime >= max(path.stat().st_mtime for path in sources()):
+        return library
     BUILD.mkdir(exist_ok=True)
     csrc = link_tree()
-    objects = BUILD / "obj"
+    objects = BUILD / ("obj_asan" if sanitize else "obj")
+    flags = FLAGS + (["-fsanitize=address", "-fno-omit-frame-pointer", "-g1", "-DSIMT_SANITIZE=1"] if sanitize else [])
     objects.mkdir(exist_ok=True)
     jobs = [(csrc / "engine.cu", objects / "engine.o", []), (csrc / "myers.cu", objects / "myers.o", []),
             (HERE / "simt.cpp", objects / "simt.o", [])]
@@ -67,7 +68,7 @@ def build(verbose: bool = False) -> Path:
 
     def compile_one(job):
         source, output, extra = job
-        command = ["g++", *FLAGS, *extra, "-c", str(source), "-o", str(output)]
+        command = ["g++", *flags, *extra, "-c", str(source), "-o", str(output)]
         done = subprocess.run(command, capture_output=True, text=True)
         if done.returncode != 0:
             raise RuntimeError(f"{' '.join(command)}\n{done.stderr[-6000:]}")
@@ -77,11 +78,12 @@ def build(verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1))) as pool:
         compiled = list(pool.map(compile_one, jobs))
-    temporary = LIBRARY.with_suffix(".so.tmp")
-    subprocess.run(["g++", "-shared", "-o", str(temporary), *map(str, compiled), "-lpthread", "-ldl"], check=True)
-    temporary.replace(LIBRARY)
-    return LIBRARY
+    temporary = library.with_suffix(".so.tmp")
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address"] if sanitize else []), "-o", str(temporary), *map(str, compiled),
+                    "-lpthread", "-ldl"], check=True)
+    temporary.replace(library)
+    return library
 
 
 if __name__ == "__main__":
-    print(build(verbose=True))
+    print(build(verbose=True, sanitize="--sanitize" in sys.argv))

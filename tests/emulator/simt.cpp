@@ -24,6 +24,13 @@
 #error "the fiber switch below is written for x86-64"
 #endif
 
+/* `build.py --sanitize` (AddressSanitizer): device allocations become exact-size heap blocks, the part of the CTA's shared
+ * memory a launch did not ask for is poisoned, and the fiber switches are announced to the sanitizer. */
+#if defined(SIMT_SANITIZE)
+#include <sanitizer/asan_interface.h>
+#include <sanitizer/common_interface_defs.h>
+#endif
+
 extern "C" void simt_switch(void **save_stack_pointer, void *load_stack_pointer);
 asm(R"(
 .text
@@ -83,6 +90,8 @@ struct Machine {
     unsigned threads = 0, live_threads = 0, barrier_arrived = 0, running = 0;
     uint64_t barrier_generation = 0;
     void *scheduler_stack_pointer = nullptr;
+    void const *scheduler_stack_bottom = nullptr; // sanitizer builds only
+    size_t scheduler_stack_size = 0;
     void (*body)(void *) = nullptr;
     void *context = nullptr;
     bool inside_kernel = false;
@@ -98,12 +107,22 @@ std::mutex launch_mutex; // host threads of a device group launch concurrently; 
 
 void yield_to_scheduler() {
     Fiber &self = machine.fibers[machine.running];
+#if defined(SIMT_SANITIZE)
+    void *fake = nullptr;
+    __sanitizer_start_switch_fiber(self.wait == Wait::kDone ? nullptr : &fake, machine.scheduler_stack_bottom, machine.scheduler_stack_size);
+#endif
     simt_switch(&self.stack_pointer, machine.scheduler_stack_pointer);
+#if defined(SIMT_SANITIZE)
+    __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
 }
 
 void leave_warp(Warp &warp);
 
 void fiber_main() {
+#if defined(SIMT_SANITIZE)
+    __sanitizer_finish_switch_fiber(nullptr, &machine.scheduler_stack_bottom, &machine.scheduler_stack_size);
+#endif
     machine.body(machine.context);
     Fiber &self = machine.fibers[machine.running];
     self.wait = Wait::kDone;
@@ -168,7 +187,14 @@ void run_cta(unsigned block) {
                     machine.fibers[t].wait = Wait::kNone;
                     machine.running = t;
                     current_thread = {t, 0, 0};
+#if defined(SIMT_SANITIZE)
+                    void *fake = nullptr;
+                    __sanitizer_start_switch_fiber(&fake, machine.stacks + (size_t)t * kStackBytes, kStackBytes);
+#endif
                     simt_switch(&machine.scheduler_stack_pointer, machine.fibers[t].stack_pointer);
+#if defined(SIMT_SANITIZE)
+                    __sanitizer_finish_switch_fiber(fake, nullptr, nullptr);
+#endif
                     warp_moved = moved = true;
                 }
             }
@@ -195,6 +221,10 @@ void launch(unsigned grid, unsigned threads, size_t shared_bytes, void (*body)(v
     current_block_dim = {threads, 1, 1}, current_grid_dim = {grid, 1, 1};
     static bool const trace = getenv("SZB_EMULATOR_TRACE") != nullptr;
     if (trace) std::fprintf(stderr, "[simt emulator] launch: %u CTAs of %u threads, %zu bytes of shared memory\n", grid, threads, shared_bytes);
+#if defined(SIMT_SANITIZE)
+    __asan_unpoison_memory_region(machine.shared, kSharedBytes);
+    __asan_poison_memory_region(machine.shared + shared_bytes, kSharedBytes - shared_bytes);
+#endif
     for (unsigned block = 0; block < grid; ++block) run_cta(block);
     if (trace) std::fprintf(stderr, "[simt emulator] launch finished\n");
     machine.inside_kernel = false;
@@ -271,11 +301,19 @@ std::mutex allocations_mutex;
 
 cudaError_t allocate(void **pointer, size_t bytes, cudaMemoryType type) {
     // Guard bytes on both sides: vector loads and bulk copies touch the 16-byte windows around a buffer's ends.
+#if defined(SIMT_SANITIZE)
+    size_t const rounded = bytes ? bytes : 1; // exact: the sanitizer's red zones sit right behind the last byte
+    void *block = nullptr;
+    if (posix_memalign(&block, 256, rounded) != 0) return cudaErrorMemoryAllocation;
+    memset(block, 0xA5, rounded);
+    *pointer = block;
+#else
     size_t const rounded = (bytes + 255) & ~(size_t)255;
     void *block = nullptr;
     if (posix_memalign(&block, 256, rounded + 512) != 0) return cudaErrorMemoryAllocation;
     memset(block, 0xA5, rounded + 512); // reading uninitialised device memory should not look like zeros
     *pointer = static_cast<char *>(block) + 256;
+#endif
     std::lock_guard<std::mutex> lock(allocations_mutex);
     allocations[reinterpret_cast<uintptr_t>(*pointer)] = {rounded, type};
     return cudaSuccess;
@@ -287,7 +325,11 @@ cudaError_t release(void *pointer) {
         std::lock_guard<std::mutex> lock(allocations_mutex);
         if (!allocations.erase(reinterpret_cast<uintptr_t>(pointer))) return cudaErrorInvalidValue;
     }
+#if defined(SIMT_SANITIZE)
+    free(pointer);
+#else
     free(static_cast<char *>(pointer) - 256);
+#endif
     return cudaSuccess;
 }
 
