@@ -85,5 +85,18 @@ def build(verbose: bool = False, sanitize: bool = False) -> Path:
     return library
 
 
+def build_nccl() -> Path:
+    """`libnccl_emulated.so`: NCCL's entry points over host threads of one process (nccl_threads.cpp), found by the emulated
+    library through SZS_B200_NCCL_LIBRARY — so that the multi-rank exchange runs on the CPU tier with ranks as threads."""
+    library, source = BUILD / "libnccl_emulated.so", HERE / "nccl_threads.cpp"
+    if library.exists() and library.stat().st_mtime >= max(source.stat().st_mtime, (HERE / "include" / "nccl.h").stat().st_mtime):
+        return library
+    BUILD.mkdir(exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-fvisibility=hidden", "-shared", f"-I{HERE / 'include'}", str(source),
+                    "-o", str(library), "-lpthread"], check=True)
+    return library
+
+
 if __name__ == "__main__":
+    build_nccl()
     print(build(verbose=True, sanitize="--sanitize" in sys.argv))

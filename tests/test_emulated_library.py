@@ -82,3 +82,18 @@ def test_gpu_parity_suite_on_the_emulated_library(emulated_library):
     summary = re.search(r"(\d+) passed", ran.stdout)
     assert summary and int(summary.group(1)) >= 113, tail
     assert "failed" not in ran.stdout and "error" not in ran.stdout.lower(), tail
+
+
+def test_multi_rank_exchange_with_ranks_as_threads(emulated_library):
+    """`szs_b200_comm_scores_u64tape` for worlds of 2 and 3 ranks on the CPU tier: every rank is a thread on the emulated
+    device, NCCL is the thread-backed stand-in of tests/emulator/nccl_threads.cpp (found through SZS_B200_NCCL_LIBRARY, the
+    way a real NCCL is). Covers the packed broadcast, the row partition, the grouped gather, symmetric calls with
+    asymmetric tables, more ranks than rows, and rejections travelling in the header."""
+    from tests.emulator import build as emulator_build
+
+    support.build_oracle()
+    environment = dict(os.environ, SZS_B200_LIBRARY=str(emulated_library), SZS_B200_NCCL_LIBRARY=str(emulator_build.build_nccl()),
+                       SZB_EMULATED_SMS="2")
+    ran = subprocess.run([sys.executable, "tests/emulator/ranks_as_threads.py"], cwd=support.ROOT, env=environment,
+                         capture_output=True, text=True, timeout=900)
+    assert ran.returncode == 0 and "world 2: ok" in ran.stdout and "world 3: ok" in ran.stdout, (ran.stdout + ran.stderr)[-3000:]
