@@ -176,13 +176,34 @@ void run_cta(unsigned block) {
                 warp.deposits[phase][lane] = 0, warp.kinds[phase][lane] = 0, warp.tags[phase][lane] = ~0ull;
     }
     for (unsigned t = 0; t < threads; ++t) prepare_fiber(t);
+    // SZB_EMULATOR_SHUFFLE=<seed>: warps and lanes take their turns in a pseudo-random order that changes all the time.
+    // Properly synchronised kernels compute the same thing under every order; one that leans on an accident of the default
+    // order (a missing barrier, a read before a neighbour's write) shows up as a parity failure.
+    static char const *const shuffle_text = getenv("SZB_EMULATOR_SHUFFLE");
+    static uint64_t shuffle_state = shuffle_text ? strtoull(shuffle_text, nullptr, 10) * 2654435761ull + 1 : 0;
+    auto next_random = [&]() -> unsigned {
+        shuffle_state = shuffle_state * 6364136223846793005ull + 1442695040888963407ull;
+        return (unsigned)(shuffle_state >> 33);
+    };
     while (machine.live_threads) {
         bool moved = false;
-        for (unsigned w = 0; w < n_warps; ++w) {
+        unsigned const warp_offset = shuffle_text ? next_random() % n_warps : 0, warp_stride = shuffle_text ? (next_random() | 1u) : 1;
+        for (unsigned turn = 0; turn < n_warps; ++turn) {
+            // (n_warps is a power of two for every kernel of the library, so an odd stride visits each warp once; other
+            // sizes fall back to the plain order.)
+            unsigned const w = (n_warps & (n_warps - 1)) ? turn : (warp_offset + turn * warp_stride) % n_warps;
             // Lanes of one warp take turns until none of them can move: most synchronisation is warp-level.
             for (bool warp_moved = true; warp_moved;) {
                 warp_moved = false;
-                for (unsigned t = w * 32; t < std::min(threads, (w + 1) * 32); ++t) {
+                unsigned const lane_offset = shuffle_text ? next_random() & 31 : 0, lane_stride = shuffle_text ? (next_random() | 1u) & 31 : 1;
+                for (unsigned step = 0; step < 32; ++step) {
+                    unsigned const t = w * 32 + ((lane_offset + step * lane_stride) & 31);
+                    if (t >= threads) continue;
+                    // With shuffling on, a runnable lane is sometimes passed over: neighbours then overtake it.
+                    if (shuffle_text && (next_random() & 7) == 0) {
+                        if (runnable(t)) warp_moved = moved = true;
+                        continue;
+                    }
                     if (!runnable(t)) continue;
                     machine.fibers[t].wait = Wait::kNone;
                     machine.running = t;
@@ -197,6 +218,8 @@ void run_cta(unsigned block) {
 #endif
                     warp_moved = moved = true;
                 }
+                // ... and a warp sometimes yields to the others in the middle of its work (between two collectives).
+                if (shuffle_text && (next_random() & 3) == 0) break;
             }
         }
         if (!moved && machine.live_threads) die("deadlock: no thread of the CTA can make progress");

@@ -68,10 +68,16 @@ def test_emulated_library_exports_the_abi(emulated_library):
     assert lib.szs_capabilities_runtime() & _abi.CAP_CUDA
 
 
-def test_gpu_parity_suite_on_the_emulated_library(emulated_library):
+@pytest.mark.parametrize("schedule", ["in_order", "shuffled"])
+def test_gpu_parity_suite_on_the_emulated_library(schedule, emulated_library):
+    """`shuffled`: warps and lanes take their turns in a pseudo-random, ever-changing order (SZB_EMULATOR_SHUFFLE) and on a
+    one-SM device. Correctly synchronised kernels compute the same under every order; a kernel that leans on an accident
+    of the default order — a missing barrier, a read ahead of a neighbour's write — fails parity here."""
     support.build_oracle()
     expression = " or ".join(f"({name})" for name in SELECTED)
     environment = dict(os.environ, SZS_B200_LIBRARY=str(emulated_library), SZB_EMULATED_SMS="2")
+    if schedule == "shuffled":
+        environment.update(SZB_EMULATOR_SHUFFLE="20260923", SZB_EMULATED_SMS="1")
     command = [sys.executable, "-m", "pytest", "tests/test_parity_gpu.py", "tests/test_multi_gpu.py", "-m", "gpu", "-q", "-x",
                "-p", "no:cacheprovider", "-k", expression]
     if importlib.util.find_spec("xdist"):  # every worker process loads its own emulator
