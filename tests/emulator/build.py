@@ -60,7 +60,7 @@ def build(verbose: bool = False, sanitize: bool = False) -> Path:
     BUILD.mkdir(exist_ok=True)
     csrc = link_tree()
     objects = BUILD / ("obj_asan" if sanitize else "obj")
-    flags = FLAGS + (["-fsanitize=address", "-fno-omit-frame-pointer", "-g1", "-DSIMT_SANITIZE=1"] if sanitize else [])
+    flags = FLAGS + (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-g1", "-DSIMT_SANITIZE=1"] if sanitize else [])
     objects.mkdir(exist_ok=True)
     jobs = [(csrc / "engine.cu", objects / "engine.o", []), (csrc / "myers.cu", objects / "myers.o", []),
             (HERE / "simt.cpp", objects / "simt.o", [])]
@@ -79,7 +79,7 @@ def build(verbose: bool = False, sanitize: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1))) as pool:
         compiled = list(pool.map(compile_one, jobs))
     temporary = library.with_suffix(".so.tmp")
-    subprocess.run(["g++", "-shared", *(["-fsanitize=address"] if sanitize else []), "-o", str(temporary), *map(str, compiled),
+    subprocess.run(["g++", "-shared", *(["-fsanitize=address,undefined"] if sanitize else []), "-o", str(temporary), *map(str, compiled),
                     "-lpthread", "-ldl"], check=True)
     temporary.replace(library)
     return library

@@ -26,15 +26,17 @@ inline uint32_t opaque_two() { return 2; }
 inline uint32_t shared_window_address(void const *pointer) {
     return (uint32_t)((char const *)pointer - (char const *)simt::dynamic_shared());
 }
+void misaligned_shared_load(uint32_t address, uint32_t bytes);
 inline uint32_t load_shared_word(uint32_t address) {
-    uint32_t word;
-    memcpy(&word, (char const *)simt::dynamic_shared() + address, 4);
-    return word;
+    if (address & 3u) misaligned_shared_load(address, 4); // the hardware faults on a misaligned ld.shared
+    return *(uint32_t const *)((char const *)simt::dynamic_shared() + address);
 }
 inline void load_shared_pair(uint32_t address, uint32_t &first, uint32_t &second) {
+    if (address & 7u) misaligned_shared_load(address, 8);
     first = load_shared_word(address), second = load_shared_word(address + 4);
 }
 inline void load_shared_quad(uint32_t address, uint32_t &first, uint32_t &second, uint32_t &third, uint32_t &fourth) {
+    if (address & 15u) misaligned_shared_load(address, 16);
     first = load_shared_word(address), second = load_shared_word(address + 4);
     third = load_shared_word(address + 8), fourth = load_shared_word(address + 12);
 }

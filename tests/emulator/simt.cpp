@@ -300,6 +300,10 @@ uint32_t const *exchange(uint32_t value, int kind) {
 } // namespace simt
 
 namespace szb {
+void misaligned_shared_load(uint32_t address, uint32_t bytes) {
+    std::fprintf(stderr, "[simt emulator] ld.shared of %u bytes at shared address %u is misaligned\n", bytes, address);
+    std::abort();
+}
 void bulk_copy_alignment_violation() {
     std::fprintf(stderr, "[simt emulator] cp.async.bulk needs 16-byte aligned source, destination and size\n");
     std::abort();
