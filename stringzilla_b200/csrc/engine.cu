@@ -1238,13 +1238,7 @@ static Failure build_schedule(Engine const &engine, Model const &model, StagedSe
     host_slots.clear();
     host_slots.reserve(n_dp_candidates);
     uint64_t &cells_total = schedule.cells_total = 0, &cells_u16 = schedule.cells_u16 = 0;
-    // Register budget (128 per thread) caps the strip width per family: packed affine recurrences keep two strips per
-    // lane (36 columns), the 32-bit tier adds the strip's symbols for compare mode (32 linear / 20 affine).
-    auto widest_strip = [](int family) {
-        if (family == FAM_LIN_COMPARE) return 32; // strip cells + strip bytes
-        if (family >= FAM_S32_GLOBAL_LIN) return family_is_affine(family) ? 20 : 32;
-        return family_is_affine(family) ? 36 : 40;
-    };
+    // Strips wider than `widest_strip(family)` (launch.cuh) do not exist: such slots take equal passes of the widest one.
     auto shape_of = [&](int family, uint32_t longest) {
         Shape shape = shape_for_length(longest, latency_lanes >= 16 ? 32 : 8);
         int const cap = widest_strip(family);

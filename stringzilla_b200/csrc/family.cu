@@ -13,7 +13,17 @@
 namespace szb {
 
 template <int FAM, int STRIP>
+static cudaError_t launch_reachable_strip(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args);
+
+template <int FAM, int STRIP>
 static cudaError_t launch_strip(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
+    // Strips beyond the family's register budget are never scheduled (widest_strip, launch.cuh) and not instantiated.
+    if constexpr (kStrips[STRIP] > widest_strip(FAM)) return cudaErrorInvalidValue;
+    else return launch_reachable_strip<FAM, STRIP>(grid, smem, stream, args);
+}
+
+template <int FAM, int STRIP>
+static cudaError_t launch_reachable_strip(int grid, size_t smem, cudaStream_t stream, KernelArgs const &args) {
     auto kernel = wavefront_kernel<FAM, kStrips[STRIP]>;
     // Opt in to the large dynamic shared-memory carve-out once per kernel and device.
     // Engines on different host threads launch concurrently: one atomic bit per device; devices past the mask are

@@ -52,7 +52,16 @@ inline size_t shared_bytes(int strip_index, int n_classes, bool compare) {
     return 16 + 1024 + 2 * kStageBytes + profile;
 }
 
-inline bool family_is_affine(int family) { return family == 1 || family == 3 || family == 5 || family == 7; }
+constexpr bool family_is_affine(int family) { return family == 1 || family == 3 || family == 5 || family == 7; }
+
+/** The widest register strip a family is instantiated for and the scheduler may pick. The 128-register budget sets it:
+ *  packed affine recurrences keep two strips per lane (36 columns), the 32-bit tier adds the strip's symbols for compare
+ *  mode (32 columns linear, 20 affine), and so does the packed byte-compare family (32). */
+constexpr int widest_strip(int family) {
+    if (family == FAM_LIN_COMPARE) return 32;
+    if (family >= FAM_S32_GLOBAL_LIN) return family_is_affine(family) ? 20 : 32;
+    return family_is_affine(family) ? 36 : 40;
+}
 
 template <int FAM>
 cudaError_t launch_family(int strip_index, int grid, size_t smem, cudaStream_t stream, KernelArgs const &args);

@@ -610,3 +610,70 @@ def test_large_pageable_corpus_is_staged_in_parallel(scope):
     weird = szb.LevenshteinDistances(1, 3, 3, 3)
     few = support.random_strings(rng, 3, 100, 200, support.DNA)
     assert np.array_equal(weird(tape, few, device=scope), support.oracle_levenshtein(tape, few, 1, 3, 3, 3))
+
+
+# One engine per recurrence family of kernels.cuh, with the widest register strip the scheduler allows it (launch.cuh).
+def _family_engines():
+    byte_to_class, blosum = scoring.blosum62()
+    binary_classes, heavy = scoring.uniform(b"ab", 100, -100)
+    text = bytes(range(33, 113))  # 80 distinct bytes: byte-compare recurrences
+    weighted = lambda table_classes, table, local: (
+        lambda open, extend: (lambda q, c: support.oracle_weighted(q, c, table_classes, table, open, extend, local)))
+    return [
+        ("lin_shift", szb.LevenshteinDistances(1, 3, 3, 3), support.DNA, 40,
+         lambda q, c: support.oracle_levenshtein(q, c, 1, 3, 3, 3)),
+        ("aff_shift", szb.LevenshteinDistances(1, 3, 4, 2), support.DNA, 36,
+         lambda q, c: support.oracle_levenshtein(q, c, 1, 3, 4, 2)),
+        ("sw_lin", szb.SmithWatermanScores(byte_to_class, blosum, open=-4, extend=-4), support.PROTEIN, 40,
+         weighted(byte_to_class, blosum, True)(-4, -4)),
+        ("sw_aff", szb.SmithWatermanScores(byte_to_class, blosum, open=-4, extend=-1), support.PROTEIN, 36,
+         weighted(byte_to_class, blosum, True)(-4, -1)),
+        ("s32_global_lin", szb.NeedlemanWunschScores(binary_classes, heavy, open=-127, extend=-127), b"ab", 32,
+         weighted(binary_classes, heavy, False)(-127, -127)),
+        ("s32_global_aff", szb.NeedlemanWunschScores(byte_to_class, blosum, open=-2, extend=1), support.PROTEIN, 20,
+         weighted(byte_to_class, blosum, False)(-2, 1)),
+        ("s32_local_lin", szb.SmithWatermanScores(byte_to_class, blosum, open=1, extend=1), support.PROTEIN, 32,
+         weighted(byte_to_class, blosum, True)(1, 1)),
+        ("s32_local_aff", szb.SmithWatermanScores(byte_to_class, blosum, open=-2, extend=1), support.PROTEIN, 20,
+         weighted(byte_to_class, blosum, True)(-2, 1)),
+        ("lin_compare", szb.LevenshteinDistances(1, 3, 3, 3), text, 32,
+         lambda q, c: support.oracle_levenshtein(q, c, 1, 3, 3, 3)),
+    ]
+
+
+@pytest.mark.parametrize("family", range(9), ids=[entry[0] for entry in _family_engines()])
+def test_every_strip_width_of_every_family(family, scope):
+    """Every instantiation `wavefront_kernel<family, K>` the scheduler can pick. A strip of K columns is chosen for the
+    candidates whose length K x G covers most tightly, and a call too small to fill the device takes G = 32 lanes whatever
+    the length — so each strip width gets one candidate just under K x 32 and one just under K x 8 (one of the two lands on
+    it, depending on the device's size), in separate calls so that no launch is folded into a wider one."""
+    name, engine, alphabet, widest, oracle = _family_engines()[family]
+    rng = np.random.default_rng(700 + family)
+    queries = support.random_strings(rng, 5, 150, 330, alphabet) + [b"", alphabet[:1]]
+    for strip in range(8, widest + 1, 4):
+        for lanes in (32, 8):
+            top = strip * lanes
+            candidates = [support.random_strings(rng, 1, n, n, alphabet)[0] for n in (top, top - 1, top - 3, max(top - 4 * lanes + 1, 1))]
+            candidates += support.mutated_copies(rng, [queries[0]], 0.2, alphabet)  # something similar, so scores vary
+            candidates = [c[:top] for c in candidates]  # nothing longer than the strip under test
+            got = engine(queries, candidates, device=scope)
+            assert np.array_equal(got, oracle(queries, candidates)), (name, strip, lanes)
+
+
+@pytest.mark.parametrize("table", ["per_warp", "per_cta"])
+def test_every_word_count_of_the_bit_parallel_kernels(table, scope):
+    """Every instantiation `myers_kernel<W>` / `myers_shared_kernel<W>`, W = 1 .. 10 words per lane: launches of one call are
+    folded into the widest one, so each W gets calls of its own whose longest candidate needs exactly W words — at 32 lanes
+    (a small call on a large device) and at 4 lanes (the tightest shape)."""
+    alphabet = support.DNA if table == "per_warp" else bytes(range(33, 113))
+    rng = np.random.default_rng(800 + len(alphabet))
+    queries = support.random_strings(rng, 9, 0, 700, alphabet) + [b""]
+    engine = szb.LevenshteinDistances()
+    for words in range(1, 11):
+        for lanes in (32, 4):
+            top = 32 * words * lanes
+            candidates = [support.random_strings(rng, 1, n, n, alphabet)[0] for n in (top, top - 1, top - 31, top - 33)]
+            candidates += [queries[1][:top], b""]
+            got = engine(queries, candidates, device=scope)
+            assert np.array_equal(got, support.oracle_levenshtein(queries, candidates)), (table, words, lanes)
+            assert engine.last_call_stats.pairs_bit_parallel > 0
