@@ -677,3 +677,54 @@ def test_every_word_count_of_the_bit_parallel_kernels(table, scope):
             got = engine(queries, candidates, device=scope)
             assert np.array_equal(got, support.oracle_levenshtein(queries, candidates)), (table, words, lanes)
             assert engine.last_call_stats.pairs_bit_parallel > 0
+
+
+def test_malformed_calls_are_refused_and_leave_the_engine_usable(scope):
+    """Status codes of the reference's contract (stringzillas.h / types.h:810-833) for inputs the library must not score:
+    decreasing or missing offsets, a missing result matrix, a row stride below the candidate count, a handle of another
+    family, pairs too long for 32-bit cells. After every refusal the same engine scores a valid call."""
+    rng = np.random.default_rng(61)
+    queries = support.random_strings(rng, 4, 1, 40, support.DNA)
+    candidates = support.random_strings(rng, 3, 1, 40, support.DNA)
+    want = support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3)
+    engine = szb.LevenshteinDistances(1, 3, 3, 3)
+    lib = _abi.bind()
+    q, c = szb.Tape(queries), szb.Tape(candidates)
+    message = ct.c_char_p()
+    out = np.zeros((4, 3), dtype=np.uint64)
+
+    def call(tq, tc, results, stride, function=lib.szs_levenshtein_distances_u64tape, handle=None):
+        return function(handle or engine._handle, scope.handle, tq, tc, results, stride, ct.byref(message))
+
+    def still_works():
+        out[:] = 0
+        assert call(q.pointer(), c.pointer(), out.ctypes.data, 3) == 0 and np.array_equal(out, want)
+
+    still_works()
+    backwards = q.offsets.copy()
+    backwards[1] = backwards[2] + 1  # the third offset now lies before the second
+    broken = _abi.SequenceU64Tape(q.data.ctypes.data, backwards.ctypes.data, len(q))
+    assert call(ct.byref(broken), c.pointer(), out.ctypes.data, 3) == -15 and b"decrease" in message.value
+    still_works()
+    missing = _abi.SequenceU64Tape(q.data.ctypes.data, None, len(q))
+    assert call(ct.byref(missing), c.pointer(), out.ctypes.data, 3) == -15 and b"null" in message.value
+    still_works()
+    assert call(q.pointer(), c.pointer(), None, 3) == -15 and b"null" in message.value
+    still_works()
+    assert call(q.pointer(), c.pointer(), out.ctypes.data, 2) == -15 and b"stride" in message.value
+    still_works()
+    # A Levenshtein handle passed to the Needleman-Wunsch entry point.
+    assert call(q.pointer(), c.pointer(), out.ctypes.data, 3, function=lib.szs_needleman_wunsch_scores_u64tape) != 0
+    assert b"another algorithm" in message.value
+    still_works()
+    # (m + n + 4) x the largest cost magnitude must stay below 2^27 for the 32-bit tier: refused before anything runs.
+    heavy = szb.LevenshteinDistances(0, 127, 127, 127)
+    long_q, long_c = szb.Tape([b"a" * 600_000]), szb.Tape([b"b" * 500_000])
+    one = np.zeros((1, 1), dtype=np.uint64)
+    assert call(long_q.pointer(), long_c.pointer(), one.ctypes.data, 1, handle=heavy._handle) == -14  # sz_overflow_risk_k
+    assert b"32-bit" in message.value
+    assert call(q.pointer(), c.pointer(), out.ctypes.data, 3, handle=heavy._handle) == 0
+    assert np.array_equal(out, support.oracle_levenshtein(queries, candidates, 0, 127, 127, 127))
+    # Empty sides are not errors: nothing is written, nothing is read.
+    empty = szb.Tape([])
+    assert call(empty.pointer(), c.pointer(), None, 3) == 0 and call(q.pointer(), empty.pointer(), None, 0) == 0
