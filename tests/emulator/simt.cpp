@@ -442,3 +442,12 @@ cudaError_t cudaEventDestroy(cudaEvent_t event) { return free(event), cudaSucces
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) {
     api_trace("cudaEventRecord"); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float *milliseconds, cudaEvent_t, cudaEvent_t) { return *milliseconds = 0.f, cudaSuccess; }
+
+/* ---- Hooks for tests: "device" memory a Python test can fill and read back (what torch tensors do on a real GPU) ----- */
+
+extern "C" __attribute__((visibility("default"))) void *simt_device_alloc(size_t bytes) {
+    void *pointer = nullptr;
+    return cudaMalloc(&pointer, bytes) == cudaSuccess ? pointer : nullptr;
+}
+extern "C" __attribute__((visibility("default"))) void simt_device_free(void *pointer) { cudaFree(pointer); }
+

@@ -119,3 +119,36 @@ def mutated_copies(rng: np.random.Generator, strings: list[bytes], rate: float, 
 
 def have_reference() -> bool:
     return REFERENCE_LIBRARY.exists()
+
+
+class DeviceBuffer:
+    """A copy of a numpy array in DEVICE memory: a torch CUDA tensor on a GPU box, memory of the emulated device
+    (tests/emulator, `simt_device_alloc`) when the tests run against the emulated library."""
+
+    def __init__(self, array: np.ndarray):
+        from stringzilla_b200 import _abi
+
+        array = np.ascontiguousarray(array)
+        self.shape, self.dtype, self.nbytes = array.shape, array.dtype, max(array.nbytes, 1)
+        self._lib = _abi.bind()
+        if hasattr(self._lib, "simt_device_alloc"):
+            self._lib.simt_device_alloc.restype, self._lib.simt_device_alloc.argtypes = ct.c_void_p, [ct.c_uint64]
+            self._lib.simt_device_free.restype, self._lib.simt_device_free.argtypes = None, [ct.c_void_p]
+            self._tensor, self.pointer = None, self._lib.simt_device_alloc(self.nbytes)
+            ct.memmove(self.pointer, array.ctypes.data, array.nbytes)
+        else:
+            import torch
+
+            self._tensor = torch.from_numpy(array.view(np.uint8).reshape(-1).copy()).cuda()
+            self.pointer = self._tensor.data_ptr()
+
+    def numpy(self) -> np.ndarray:
+        if self._tensor is not None:
+            return self._tensor.cpu().numpy().view(self.dtype).reshape(self.shape)
+        return np.frombuffer(ct.string_at(self.pointer, int(np.prod(self.shape)) * self.dtype.itemsize), dtype=self.dtype).reshape(self.shape).copy()
+
+    def __del__(self):
+        if getattr(self, "_tensor", None) is None and getattr(self, "pointer", None):
+            self._lib.simt_device_free(self.pointer)
+            self.pointer = None
+

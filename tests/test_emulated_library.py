@@ -9,8 +9,9 @@ multi-pass hand-over, match tables, harvest, the scheduler's shapes and jobs, ro
 with the oracle and with the reference's golden vectors on every machine, GPU or not.
 
 The parity tests themselves are the GPU suite's, unchanged: they run here in a subprocess whose `SZS_B200_LIBRARY` points
-at the emulated build. Left out: tests that need real CUDA memory through torch, the two that link against the real
-library, and the ones too heavy for an emulator (a 100k-character pair, full-size tiles, retrieval corpora).
+at the emulated build. Device memory comes from a hook of the emulated device
+(`support.DeviceBuffer`; torch tensors on a real GPU). Left out: the tests that link against the real library or need two
+physical devices, and the ones too heavy for an emulator (a 100k-character pair, full-size tiles, retrieval corpora).
 """
 
 import importlib.util
@@ -40,7 +41,9 @@ SELECTED = [
     "test_unusual_cost_signs_take_the_literal_tier",
     "test_utf8_levenshtein_rune_level",
     "test_every_input_layout_of_the_abi",
-    "test_callback_sequences_outside_host_memory and unified_memory",
+    "test_callback_sequences_outside_host_memory",
+    "test_memory_kinds_and_tape_slices",
+    "test_inputs_too_large_for_the_host_side_shortcuts",
     "test_randomized_differential",
     "test_arrow_arrays_as_inputs",
     "test_row_shards_reassemble_the_matrix",
@@ -89,7 +92,7 @@ def test_gpu_parity_suite_on_the_emulated_library(schedule, emulated_library):
     tail = (ran.stdout + ran.stderr)[-4000:]
     assert ran.returncode == 0, tail
     summary = re.search(r"(\d+) passed", ran.stdout)
-    assert summary and int(summary.group(1)) >= 125, tail
+    assert summary and int(summary.group(1)) >= 128, tail
     assert "failed" not in ran.stdout and "error" not in ran.stdout.lower(), tail
 
 

@@ -358,10 +358,8 @@ def test_callback_sequences_outside_host_memory(memory, scope):
         base = lib.szs_unified_alloc(len(blob))
         ct.memmove(base, blob, len(blob))
     else:
-        import torch
-
-        device_blob = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
-        base = device_blob.data_ptr()
+        device_blob = support.DeviceBuffer(np.frombuffer(blob, dtype=np.uint8))
+        base = device_blob.pointer
     sq, keep_q = sequence_in(queries, base)
     sc, keep_c = sequence_in(candidates, base + split)
     got = np.zeros_like(want)
@@ -430,8 +428,6 @@ def test_c_program_against_the_reference_header(scope):
 def test_memory_kinds_and_tape_slices(scope):
     """Inputs and outputs in device memory, in managed memory (`szs_unified_alloc`, what the reference's Python binding
     uses), and tapes whose first offset is not zero (a slice of a larger Arrow array)."""
-    import torch
-
     rng = np.random.default_rng(53)
     strings = support.random_strings(rng, 14, 0, 200, support.PROTEIN)
     whole = szb.Tape(strings)
@@ -454,10 +450,18 @@ def test_memory_kinds_and_tape_slices(scope):
     call(whole.data.ctypes.data, host_out.ctypes.data)
     assert np.array_equal(host_out, want)
 
-    device_data = torch.from_numpy(whole.data).cuda()
-    device_out = torch.zeros((6, 9), dtype=torch.int64, device="cuda")
-    call(device_data.data_ptr(), device_out.data_ptr())
-    assert np.array_equal(device_out.cpu().numpy(), want)
+    device_data = support.DeviceBuffer(whole.data)
+    device_out = support.DeviceBuffer(np.zeros((6, 9), dtype=np.int64))
+    call(device_data.pointer, device_out.pointer)
+    assert np.array_equal(device_out.numpy(), want)
+    # Offsets in device memory as well: the host reads them through a bounce copy.
+    device_q_offsets, device_c_offsets = support.DeviceBuffer(q_offsets), support.DeviceBuffer(c_offsets)
+    tq = _abi.SequenceU64Tape(device_data.pointer, device_q_offsets.pointer, 6)
+    tc = _abi.SequenceU64Tape(device_data.pointer, device_c_offsets.pointer, 9)
+    again = support.DeviceBuffer(np.zeros((6, 9), dtype=np.int64))
+    assert lib.szs_needleman_wunsch_scores_u64tape(engine._handle, scope.handle, ct.byref(tq), ct.byref(tc), again.pointer, 9,
+                                                   ct.byref(message)) == 0, message.value
+    assert np.array_equal(again.numpy(), want)
 
     managed = lib.szs_unified_alloc(int(whole.data.size))
     managed_out = lib.szs_unified_alloc(6 * 9 * 8)
@@ -728,3 +732,39 @@ def test_malformed_calls_are_refused_and_leave_the_engine_usable(scope):
     # Empty sides are not errors: nothing is written, nothing is read.
     empty = szb.Tape([])
     assert call(empty.pointer(), c.pointer(), None, 3) == 0 and call(q.pointer(), empty.pointer(), None, 0) == 0
+
+
+def test_inputs_too_large_for_the_host_side_shortcuts(scope):
+    """More text than the host scans or packs itself (256 KB packed arena, 512 KB alphabet scan): the bytes are uploaded as
+    blobs, presence flags come from the device, UTF-8 engines decode there; callback sequences are gathered through the
+    engine's pinned buffer. Many short strings keep the cross products small."""
+    rng = np.random.default_rng(67)
+    alphabet = list("abcdefgh абвгдежз αβγδεζηθ")
+    def text(n):
+        return "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=n)).encode()
+    candidates = [text(int(n)) for n in rng.integers(20, 90, size=7000)]  # ~600 KB of UTF-8
+    queries = [text(60), text(35), b"plain ascii", b""]
+    assert sum(map(len, candidates)) > 520 * 1024
+    for costs in ((0, 1, 1, 1), (1, 3, 3, 3)):
+        got = szb.LevenshteinDistancesUTF8(*costs)(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, candidates, *costs)), costs
+        got = szb.LevenshteinDistancesUTF8(*costs)(candidates[:3000], queries, device=scope)  # the large side as queries
+        assert np.array_equal(got, support.oracle_levenshtein_utf8(candidates[:3000], queries, *costs)), costs
+    byte_level = szb.LevenshteinDistances(1, 3, 3, 3)
+    assert np.array_equal(byte_level(queries, candidates, device=scope), support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3))
+    # The same volume through callback sequences (one callback pair per string).
+    lib = _abi.bind()
+    buffers = [ct.create_string_buffer(s, len(s)) if s else ct.create_string_buffer(1) for s in candidates]
+    start = _abi.SEQUENCE_START(lambda _, i: ct.addressof(buffers[i]))
+    length = _abi.SEQUENCE_LENGTH(lambda _, i: len(candidates[i]))
+    sequence = _abi.Sequence(None, len(candidates), start, length)
+    few = [ct.create_string_buffer(s, len(s)) if s else ct.create_string_buffer(1) for s in queries]
+    few_start = _abi.SEQUENCE_START(lambda _, i: ct.addressof(few[i]))
+    few_length = _abi.SEQUENCE_LENGTH(lambda _, i: len(queries[i]))
+    few_sequence = _abi.Sequence(None, len(queries), few_start, few_length)
+    got = np.zeros((len(queries), len(candidates)), dtype=np.uint64)
+    message = ct.c_char_p()
+    status = lib.szs_levenshtein_distances(byte_level._handle, scope.handle, ct.byref(few_sequence), ct.byref(sequence),
+                                           got.ctypes.data, len(candidates), ct.byref(message))
+    assert status == 0 and np.array_equal(got, support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3))
+
