@@ -74,6 +74,10 @@ for engine_type, local in ((szs.NeedlemanWunschScores, False), (szs.SmithWaterma
         want = support.oracle_weighted([p.encode() for p in proteins_q], [p.encode() for p in proteins_c], byte_to_class, table, gaps[0], gaps[1], local)
         assert got.dtype == np.int64 and np.array_equal(got, want), (engine_type.__name__, gaps)
 
+if len(sys.argv) > 3 and sys.argv[3] == "quick":  # the emulated library of the CPU tier: no c2-sized call
+    print("BINDING_OK reference CPython binding, shape and parity cases only")
+    sys.exit(0)
+
 # A managed-memory call the way the binding makes it: `Strs` swapped to the unified allocator (similarities.c:267-271)
 dna = Strs([s.decode() for s in support.random_strings(rng, 316, 960, 1088, b"ACGT")])
 other = Strs([s.decode() for s in support.random_strings(rng, 317, 960, 1088, b"ACGT")])
@@ -97,3 +101,26 @@ def test_reference_cpython_binding_over_this_library(tmp_path):
     done = subprocess.run([sys.executable, str(script), str(ROOT), str(BINDING_DIR)], capture_output=True, text=True, timeout=600)
     assert done.returncode == 0 and "BINDING_OK" in done.stdout, done.stdout[-2000:] + done.stderr[-4000:]
     print(done.stdout.strip().splitlines()[-1])
+
+
+def test_reference_cpython_binding_over_the_emulated_library(tmp_path):
+    """The same binding on the CPU test tier: the dynamic loader is pointed (LD_LIBRARY_PATH beats the binding's RUNPATH) at a
+    directory where `libstringzillas_b200.so` is the emulated build of tests/emulator — the reference's unmodified CPython
+    extension then drives the unchanged host driver and kernels under the SIMT emulator. Test infrastructure only."""
+    import os
+
+    suffix = sysconfig.get_config_var("EXT_SUFFIX")
+    if not (BINDING_DIR / f"stringzillas{suffix}").exists():
+        pytest.skip("oracle/_ref/python is not built (needs /root/reference at build time)")
+    from tests.emulator import build as emulator_build
+
+    emulated = emulator_build.build()
+    (tmp_path / "lib").mkdir()
+    (tmp_path / "lib" / "libstringzillas_b200.so").symlink_to(emulated)
+    script = tmp_path / "child.py"
+    script.write_text(CHILD)
+    environment = dict(os.environ, LD_LIBRARY_PATH=str(tmp_path / "lib"), SZB_EMULATED_SMS="2")
+    done = subprocess.run([sys.executable, str(script), str(ROOT), str(BINDING_DIR), "quick"], capture_output=True, text=True,
+                          timeout=900, env=environment)
+    assert done.returncode == 0 and "BINDING_OK" in done.stdout, done.stdout[-2000:] + done.stderr[-4000:]
+
