@@ -113,6 +113,22 @@ def test_b200_library_against_the_reference_cpu_baseline(tmp_path):
     check_known_answers(out, expected, "b200")
 
 
+@pytest.mark.skipif(not support.have_reference(), reason="oracle/_ref is not built")
+def test_emulated_library_against_the_reference_cpu_baseline(tmp_path):
+    """The same sweep on the CPU test tier, with the emulated build of the library (tests/emulator) on the accelerated arm:
+    every engine x shape of the harness compares its tiles with the reference CPU library's. Test infrastructure only."""
+    from tests.emulator import build as emulator_build
+
+    emulated = str(emulator_build.build())
+    out = run_benchmark(SZS_ACCELERATED_LIB=emulated, STRINGWARS_BATCH="1,6", SZB_EMULATED_SMS="2")
+    assert "All benchmarks finished." in out and "Mismatch" not in out and "> Errors" not in out
+    assert "levenshtein_b200_unit:q" in out and out.count("> Stress: 1 tiles compared") >= 20
+    dataset, expected = known_answers(tmp_path)
+    out = run_benchmark(SZS_ACCELERATED_LIB=emulated, SZS_BASELINE_LIB="none", STRINGWARS_STRESS="0", STRINGWARS_DATASET=str(dataset),
+                        STRINGWARS_BATCH="6", SZB_EMULATED_SMS="2")
+    check_known_answers(out, expected, "b200")
+
+
 @pytest.mark.gpu
 def test_reference_benchmark_runs_the_b200_engines(tmp_path):
     """the REFERENCE's own benchmark binary (bench/similarities.cu compiled from /root/reference by
