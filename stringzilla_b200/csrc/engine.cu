@@ -14,6 +14,7 @@
  *  There is NO CPU fallback in this file: without a usable sm_100-class device every scoring call fails loudly.
  */
 #include "../../include/stringzillas_b200.h"
+#include "host_scan.hpp"
 #include "launch.cuh"
 #include "myers.cuh"
 
@@ -860,12 +861,9 @@ static Failure resolve_symbols(Engine &engine, cudaStream_t stream, bool symmetr
         };
         if (scannable(cs) && (!need_queries || scannable(qs))) {
             auto scan = [](StagedSet const &set, uint32_t (&seen)[256]) {
-                if (set.host_view)
-                    for (uint64_t i = 0; i < set.total_bytes; ++i) seen[set.host_view[i]] = 1;
+                if (set.host_view) mark_present_bytes(set.host_view, set.total_bytes, seen);
                 else
-                    set.for_each_host_string([&](uint8_t const *start, size_t length, size_t) {
-                        for (size_t i = 0; i < length; ++i) seen[start[i]] = 1;
-                    });
+                    set.for_each_host_string([&](uint8_t const *start, size_t length, size_t) { mark_present_bytes(start, length, seen); });
             };
             scan(cs, present);
             if (need_queries) scan(qs, query_present);

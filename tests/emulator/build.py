@@ -26,7 +26,7 @@ FLAGS = ["-std=c++17", "-O1", "-g0", "-fPIC", "-fvisibility=hidden", "-w", "-x",
 
 
 def sources() -> list[Path]:
-    return sorted(CSRC.glob("*.cu*")) + sorted(CSRC.glob("*.inc")) + sorted((HERE / "include").iterdir()) + \
+    return sorted(CSRC.glob("*.cu*")) + sorted(CSRC.glob("*.inc")) + sorted(CSRC.glob("*.?pp")) + sorted((HERE / "include").iterdir()) + \
         [HERE / "simt.cpp", ROOT / "include" / "stringzillas_b200.h", Path(__file__)]
 
 
@@ -36,7 +36,7 @@ def link_tree() -> Path:
     csrc = tree / "stringzilla_b200" / "csrc"
     csrc.mkdir(parents=True, exist_ok=True)
     (tree / "include").mkdir(exist_ok=True)
-    wanted = {path.name: path for path in CSRC.iterdir() if path.suffix in (".cu", ".cuh", ".inc")}
+    wanted = {path.name: path for path in CSRC.iterdir() if path.suffix in (".cu", ".cuh", ".inc", ".cpp", ".hpp")}
     wanted["ptx.cuh"] = HERE / "include" / "ptx.cuh"
     wanted.pop("carry_chain.inc", None)  # inline PTX; the emulator's ptx.cuh states the same addition in C++
     for stale in csrc.iterdir():
@@ -63,7 +63,7 @@ def build(verbose: bool = False, sanitize: bool = False) -> Path:
     flags = FLAGS + (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-g1", "-DSIMT_SANITIZE=1"] if sanitize else [])
     objects.mkdir(exist_ok=True)
     jobs = [(csrc / "engine.cu", objects / "engine.o", []), (csrc / "myers.cu", objects / "myers.o", []),
-            (HERE / "simt.cpp", objects / "simt.o", [])]
+            (csrc / "host_scan.cpp", objects / "host_scan.o", ["-O3"]), (HERE / "simt.cpp", objects / "simt.o", [])]
     jobs += [(csrc / "family.cu", objects / f"family{family}.o", [f"-DSZB_FAMILY={family}"]) for family in FAMILIES]
 
     def compile_one(job):

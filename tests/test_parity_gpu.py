@@ -768,3 +768,17 @@ def test_inputs_too_large_for_the_host_side_shortcuts(scope):
                                            got.ctypes.data, len(candidates), ct.byref(message))
     assert status == 0 and np.array_equal(got, support.oracle_levenshtein(queries, candidates, 1, 3, 3, 3))
 
+
+
+def test_alphabet_detection_sees_late_and_rare_bytes(scope):
+    """The host scans small inputs for the byte values they contain a block at a time (host_scan.cpp): a value that turns up
+    once, at the very end, in the middle of a block or in a tail shorter than a block must still get a class of its own."""
+    rng = np.random.default_rng(71)
+    queries = support.random_strings(rng, 6, 20, 60, b"ACGTN")
+    candidates = [b"A" * 70_000 + b"C", b"A" * 999 + b"G" + b"A" * 300, b"T" * 255 + b"N", b"A" * 256, b"AC" * 128 + b"G",
+                  b"N", b"", bytes(range(65, 75)) * 30 + b"z"]
+    for costs in ((0, 1, 1, 1), (1, 3, 3, 3), (1, 3, 4, 2)):
+        got = szb.LevenshteinDistances(*costs)(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs)), costs
+        symmetric = szb.LevenshteinDistances(*costs)(candidates[1:], device=scope)
+        assert np.array_equal(symmetric, support.oracle_levenshtein(candidates[1:], None, *costs)), costs
