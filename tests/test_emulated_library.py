@@ -52,6 +52,7 @@ SELECTED = [
     "test_every_word_count_of_the_bit_parallel_kernels",
     "test_malformed_calls_are_refused_and_leave_the_engine_usable",
     "test_alphabet_detection_sees_late_and_rare_bytes",
+    "test_randomized_runes_and_row_shards",
 ]
 
 
@@ -93,7 +94,7 @@ def test_gpu_parity_suite_on_the_emulated_library(schedule, emulated_library):
     tail = (ran.stdout + ran.stderr)[-4000:]
     assert ran.returncode == 0, tail
     summary = re.search(r"(\d+) passed", ran.stdout)
-    assert summary and int(summary.group(1)) >= 129, tail
+    assert summary and int(summary.group(1)) >= 139, tail
     assert "failed" not in ran.stdout and "error" not in ran.stdout.lower(), tail
 
 

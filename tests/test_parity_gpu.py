@@ -782,3 +782,48 @@ def test_alphabet_detection_sees_late_and_rare_bytes(scope):
         assert np.array_equal(got, support.oracle_levenshtein(queries, candidates, *costs)), costs
         symmetric = szb.LevenshteinDistances(*costs)(candidates[1:], device=scope)
         assert np.array_equal(symmetric, support.oracle_levenshtein(candidates[1:], None, *costs)), costs
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomized_runes_and_row_shards(seed, scope):
+    """Seeded random configurations of what `test_randomized_differential` leaves out: the UTF-8 engine over mixed scripts
+    (ASCII only, a few dozen runes, hundreds of runes — three different representations inside the library), and matrices
+    assembled from row shards (`score_rows` over random cuts, symmetric calls included; the threaded device group)."""
+    rng = np.random.default_rng(3000 + seed)
+    scripts = ["abcdefghij ", "abcdefgh абвгдежз αβγδεζηθ 🙂🚀", "".join(chr(0x4E00 + i) for i in range(400)) + "abc"]
+    for _ in range(3):
+        script = scripts[int(rng.integers(0, len(scripts)))]
+        top = int(rng.choice([6, 40, 200, 700]))
+        text = lambda: "".join(script[i] for i in rng.integers(0, len(script), size=int(rng.integers(0, top + 1)))).encode()
+        queries = [text() for _ in range(int(rng.integers(1, 12)))]
+        candidates = None if rng.random() < 0.3 else [text() for _ in range(int(rng.integers(1, 12)))]
+        costs = (0, 1, 1, 1) if rng.random() < 0.5 else (int(rng.integers(0, 2)), int(rng.integers(1, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 6)))
+        got = szb.LevenshteinDistancesUTF8(*costs)(queries, candidates, device=scope)
+        assert np.array_equal(got, support.oracle_levenshtein_utf8(queries, candidates, *costs)), (script[:8], top, costs)
+    # Row shards: random cuts of the query rows, each shard scored on its own, must tile the whole matrix.
+    byte_to_class, table = scoring.blosum62()
+    skewed = table.copy()
+    skewed[2, 9] -= 3  # asymmetric: a symmetric call must keep the reference's (query, candidate) orientation
+    engines = [(szb.LevenshteinDistances(), support.DNA, lambda q, c: support.oracle_levenshtein(q, c)),
+               (szb.LevenshteinDistances(1, 3, 4, 2), support.DNA, lambda q, c: support.oracle_levenshtein(q, c, 1, 3, 4, 2)),
+               (szb.NeedlemanWunschScores(byte_to_class, skewed, open=-4, extend=-1), support.PROTEIN,
+                lambda q, c: support.oracle_weighted(q, c, byte_to_class, skewed, -4, -1, False)),
+               (szb.SmithWatermanScores(byte_to_class, table, open=-3, extend=-3), support.PROTEIN,
+                lambda q, c: support.oracle_weighted(q, c, byte_to_class, table, -3, -3, True))]
+    engine, alphabet, oracle = engines[seed % len(engines)]
+    queries = support.random_strings(rng, int(rng.integers(2, 40)), 0, 260, alphabet)
+    for candidates in (support.random_strings(rng, int(rng.integers(1, 20)), 0, 260, alphabet), None):
+        columns = len(queries) if candidates is None else len(candidates)
+        cuts = sorted({0, len(queries), *rng.integers(0, len(queries) + 1, size=3).tolist()})
+        out = np.zeros((len(queries), columns), dtype=engine._result_dtype)
+        for begin, end in zip(cuts, cuts[1:]):
+            engine.score_rows(queries, candidates, begin, end, device=scope, out=out)
+        want = oracle(queries, candidates)
+        if candidates is None:
+            # Shards of a symmetric call fill the cells left of their diagonal block; the caller mirrors.
+            lower = np.tril(np.ones_like(want, dtype=bool))
+            assert np.array_equal(out[lower], want[lower]), (seed, cuts)
+        else:
+            assert np.array_equal(out, want), (seed, cuts)
+        group = szb.DeviceGroup([0, 0])
+        assert np.array_equal(engine.sharded(queries, candidates, group), want), seed
