@@ -185,3 +185,23 @@ def test_random_calls_keep_the_schedule_invariants(seed):
     c = None if symmetric else _random_lengths(rng, n_candidates, longest, int(rng.integers(0, 4)))
     result = plan(engine, q, c, distinct_bytes=distinct, device_sms=device_sms)
     check_invariants(*result, symmetric=symmetric and n_queries > 1)
+
+
+def test_structural_efficiency_of_the_bench_tiles():
+    """Useful cells / executed cells (tools/structural_efficiency.py: padding up to a shape's coverage, wavefront fill and
+    drain, the shorter partner of a packed pair, multi-pass rounding) for the BASELINE tiles on a 148-SM device: a guard
+    against a scheduler change that quietly wastes cells. The measured values are in DESIGN.md §7."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("structural_efficiency", support_root() / "tools" / "structural_efficiency.py")
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    for workload, floor in (("c2", 0.93), ("c2_weird", 0.90), ("c3_sw", 0.90), ("c4", 0.88)):
+        label, value = module.efficiency(workload)
+        assert floor <= value <= 1.0, (label, value)
+
+
+def support_root():
+    from tests import support
+
+    return support.ROOT
